@@ -1,0 +1,200 @@
+/*
+ * yacrd_b200.h — C ABI of the B200-native detect path of yacrd (coverage pile-up, bad-region
+ * segmentation, Chimeric / NotCovered / NotBad classification).
+ *
+ * The reference (natir/yacrd 1.0.0, Rust) has no FFI; its seam for this path is two trait objects,
+ * `Box<dyn Reads2Ovl>` (src/reads2ovl/mod.rs:43-163) and `Box<dyn BadPart>` (src/stack.rs:35-41),
+ * driven by src/main.rs:42-84. Every entry point below names the trait item it replaces, so that a
+ * ~60-line `impl Reads2Ovl` + `impl BadPart` shim is all a maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes; no C++ or torch types cross this boundary; nothing throws.
+ *  - every function that can fail returns an int: YB_OK (0) or a negative yb_status mirroring
+ *    src/error.rs:30-92; yb_last_error(ctx) gives the message.
+ *  - a yb_ctx is single-threaded (the traits take &mut self); use one ctx per GPU / per thread.
+ *  - ids are byte strings (not NUL-terminated), copied on first sight; reads are indexed densely
+ *    in first-seen order.
+ *  - output views (gaps, ids, bitmaps) are BORROWED: valid until the next mutating call on the ctx
+ *    or yb_destroy — the same lifetime `get_bad_part` gives its `&(Vec<(u32,u32)>, usize)`.
+ *  - the compute path is CUDA (sm_100a) only. There is no CPU fallback: without a usable device
+ *    yb_create fails with YB_ERR_CUDA.
+ */
+#ifndef YACRD_B200_H
+#define YACRD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YB_VERSION "1.0.0 Magby (b200)" /* src/cli.rs:35 version string + backend tag */
+
+typedef enum yb_status {
+    YB_OK = 0,
+    YB_ERR_CANT_READ_FILE = -1,        /* error.rs: CantReadFile */
+    YB_ERR_CANT_WRITE_FILE = -2,       /* error.rs: CantWriteFile */
+    YB_ERR_UNKNOWN_FORMAT = -3,        /* error.rs: UnableToDetectFileFormat */
+    YB_ERR_WRONG_FORMAT = -4,          /* error.rs: CantRunOperationOnFile (fasta/fastq/yacrd given as overlaps) */
+    YB_ERR_READING = -5,               /* error.rs: ReadingErrorNoFilename (record does not deserialize) */
+    YB_ERR_WRITING = -6,               /* error.rs: WritingErrorNoFilename */
+    YB_ERR_CORRUPT_REPORT = -7,        /* error.rs: CorruptYacrdReport */
+    YB_ERR_MALFORMED_INTERVAL = -8,    /* new: begin >= end or end > length (SURVEY.md §7 "Malformed input") */
+    YB_ERR_INVALID_ARGUMENT = -9,
+    YB_ERR_STATE = -10,                /* call order violated (e.g. results queried before compute) */
+    YB_ERR_TOO_LARGE = -11,            /* > 2^32-16 intervals or reads in one context, or a read longer than 2^31-1 */
+    YB_ERR_CUDA = -12,
+    YB_ERR_NOMEM = -13
+} yb_status;
+
+/* src/editor/mod.rs:43-59 ReadType; also the 2-bit code in the class bitmap */
+typedef enum yb_read_type { YB_NOT_BAD = 0, YB_CHIMERIC = 1, YB_NOT_COVERED = 2 } yb_read_type;
+
+typedef struct yb_ctx yb_ctx;
+
+typedef struct yb_opts {
+    int32_t device;            /* CUDA ordinal; -1 = current device */
+    uint32_t read_buffer_size; /* --read-buffer-size (cli.rs:57-59), used by yb_init_file; 0 = 8192 */
+    uint32_t flags;            /* YB_FLAG_* */
+    uint32_t reserved;
+} yb_opts;
+
+#define YB_FLAG_KEEP_HOST_INTERVALS 1u /* keep arrival-order intervals so yb_overlap() works after upload */
+
+typedef struct yb_stats {
+    uint64_t n_reads;
+    uint64_t n_intervals;
+    uint64_t n_gaps;          /* after compute */
+    uint64_t n_not_bad, n_chimeric, n_not_covered;
+    uint64_t max_intervals_per_read;
+    uint64_t n_reads_warp, n_reads_cta, n_reads_huge; /* kernel tier each read took */
+    uint64_t kernel_launches; /* cumulative count of this library's kernel launches */
+    uint64_t h2d_bytes, d2h_bytes; /* cumulative */
+} yb_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+/* FullMemory::new (fullmemory.rs:36) + FromOverlap::new (stack.rs:51-59). NULL on failure
+ * (yb_create_error() tells why). */
+yb_ctx *yb_create(const yb_opts *opts);
+const char *yb_create_error(void);
+void yb_destroy(yb_ctx *ctx);
+/* Empties the store and the results but keeps all host/device buffers, ready for the next batch
+ * (the reference's compute_all_bad_part loops over get_overlaps batches, stack.rs:148-161). */
+int yb_reset(yb_ctx *ctx);
+const char *yb_last_error(const yb_ctx *ctx);
+const char *yb_version(void);
+const char *yb_type_name(int read_type); /* ReadType::as_str, editor/mod.rs:51-58 */
+
+/* ---- producer side: trait Reads2Ovl (reads2ovl/mod.rs:43-163) ------------------------------- */
+/* add_overlap_and_length, mod.rs:157 / fullmemory.rs:82-90: first-seen length wins. */
+int yb_add_overlap_and_length(yb_ctx *ctx, const char *id, size_t id_len, uint32_t begin,
+                              uint32_t end, uint64_t length);
+/* add_overlap, mod.rs:154 / fullmemory.rs:64-72 (length stays 0 until add_length). */
+int yb_add_overlap(yb_ctx *ctx, const char *id, size_t id_len, uint32_t begin, uint32_t end);
+/* add_length, mod.rs:155 / fullmemory.rs:74-76: sets unconditionally. */
+int yb_add_length(yb_ctx *ctx, const char *id, size_t id_len, uint64_t length);
+/* Bulk variant for pre-interned input (one get_overlaps batch, stack.rs:149): read r owns
+ * iv[2*rowptr[r] .. 2*rowptr[r+1]) as (begin,end) pairs. With ids (ids[r] / id_lens[r], id_lens may be
+ * NULL for NUL-terminated ids) the rows are merged into the named store like add_overlap_and_length.
+ * With ids == NULL the reads are named by their decimal index and the block is appended to the
+ * context's pinned CSR directly (an index-named context cannot also hold named reads). Host pointers;
+ * the data is copied. */
+int yb_add_csr(yb_ctx *ctx, const uint32_t *rowptr, const uint32_t *iv, const uint32_t *length,
+               uint32_t n_reads, const char *const *ids, const size_t *id_lens);
+/* Zero-copy variant: the context BORROWS the caller's host CSR (index-named reads, rowptr[0] == 0) until
+ * yb_destroy; allocate it with yb_host_alloc for full H2D speed. Needs an empty context. */
+int yb_bind_csr(yb_ctx *ctx, const uint32_t *rowptr, const uint32_t *iv, const uint32_t *length,
+                uint32_t n_reads);
+/* Page-locked host memory for buffers handed to yb_bind_csr. */
+void *yb_host_alloc(size_t n_bytes);
+void yb_host_free(void *p);
+/* Reads2Ovl::init, mod.rs:44-81: sniff PAF/M4 by file name (util.rs:39-55) and parse. */
+int yb_init_file(yb_ctx *ctx, const char *path);
+/* Same over an in-memory buffer; format: 'p' = PAF (tab, io.rs:24-34), 'm' = M4 (space, io.rs:37-50). */
+int yb_init_buffer(yb_ctx *ctx, const char *text, size_t n_bytes, int format);
+/* util::get_file_type (util.rs:39-55): 'm' m4/mhap, 'p' paf, 'y' yacrd, 'q' fastq, 'a' fasta, 'o' yovl,
+ * 0 unknown. */
+int yb_file_type(const char *path);
+/* Reads2Ovl::length, mod.rs:152 (0 when unknown). */
+uint64_t yb_length(const yb_ctx *ctx, const char *id, size_t id_len);
+/* Reads2Ovl::overlap, mod.rs:150: arrival-order intervals; empty when unknown. Needs
+ * YB_FLAG_KEEP_HOST_INTERVALS once the data has been uploaded. */
+int yb_overlap(yb_ctx *ctx, const char *id, size_t id_len, const uint32_t **iv_pairs,
+               uint32_t *n_intervals);
+/* get_reads (mod.rs:160 / stack.rs:171-173) as an index space in first-seen order. */
+uint32_t yb_n_reads(const yb_ctx *ctx);
+int yb_read_at(const yb_ctx *ctx, uint32_t idx, const char **id, size_t *id_len);
+int64_t yb_read_index(const yb_ctx *ctx, const char *id, size_t id_len); /* -1 when unknown */
+
+/* ---- consumer side: trait BadPart (stack.rs:35-41) ------------------------------------------ */
+/* compute_all_bad_part, stack.rs:143-162, fused with type_of_read (editor/mod.rs:85-100):
+ * host CSR -> H2D -> sm_100a kernels -> D2H of classes + bad-region lists. `coverage` is `-c`
+ * (cli.rs:49-51), `not_coverage` is `-n` (cli.rs:53-55). */
+int yb_compute_all_bad_part(yb_ctx *ctx, uint64_t coverage, double not_coverage);
+/* get_bad_part, stack.rs:164-169: unknown id => YB_OK with n_gaps = 0, length = 0, cls = NotBad. */
+int yb_get_bad_part(yb_ctx *ctx, const char *id, size_t id_len, const uint32_t **gap_pairs,
+                    uint32_t *n_gaps, uint64_t *length, uint8_t *cls);
+int yb_get_bad_part_at(yb_ctx *ctx, uint32_t idx, const uint32_t **gap_pairs, uint32_t *n_gaps,
+                       uint64_t *length, uint8_t *cls);
+/* main.rs:80-84 + editor::report (editor/mod.rs:61-83): one line per read, first-seen order. */
+int yb_write_report(yb_ctx *ctx, const char *path);
+/* Formats read idx's report line (no trailing newline) into out; returns its length or <0. */
+int64_t yb_format_report_line(yb_ctx *ctx, uint32_t idx, char *out, size_t cap);
+/* 1 byte per read (yb_read_type), and the packed 2-bit-per-read bitmap (read r lives in byte r/4,
+ * bits 2*(r%4)..+1) that the multi-GPU path all-gathers. Host views. */
+const uint8_t *yb_classes(yb_ctx *ctx, size_t *n);
+const uint8_t *yb_class_bitmap(yb_ctx *ctx, size_t *n_bytes);
+/* The whole result as a CSR of bad regions: gap_ptr[0..n_reads] and (begin,end) pairs. Host views. */
+const uint32_t *yb_gap_ptr(yb_ctx *ctx, size_t *n);
+const uint32_t *yb_gaps(yb_ctx *ctx, size_t *n_pairs);
+/* FromReport::new, stack.rs:182-215: load an existing .yacrd report instead of computing. */
+int yb_init_report(yb_ctx *ctx, const char *path);
+int yb_init_report_buffer(yb_ctx *ctx, const char *text, size_t n_bytes);
+
+/* ---- staged device API (what yb_compute_all_bad_part is made of) ---------------------------- */
+/* Freeze the host store into a CSR (flat (begin,end) buffer + row pointers + lengths), validate
+ * 0 <= begin < end <= length, and copy it to HBM. This is the get_overlaps boundary (stack.rs:149). */
+int yb_upload(yb_ctx *ctx);
+/* Kernels only; inputs and outputs stay resident in HBM. `stream` is a cudaStream_t (NULL = the
+ * context's own stream); the call is asynchronous with respect to the host. */
+int yb_compute_device(yb_ctx *ctx, uint64_t coverage, double not_coverage, void *stream);
+/* D2H of classes, bitmap, gap offsets and gaps (synchronises the stream). */
+int yb_download(yb_ctx *ctx);
+int yb_synchronize(yb_ctx *ctx);
+/* Device views for collectives / chaining (valid after yb_compute_device on the same stream). */
+void *yb_device_class_bitmap(yb_ctx *ctx, size_t *n_bytes);
+/* Make the kernels write the 2-bit bitmap straight into a caller-owned device buffer (e.g. this rank's
+ * slot of an in-place all-gather buffer); n_bytes >= 4*ceil(n_reads/16). NULL unbinds. */
+int yb_bind_device_bitmap(yb_ctx *ctx, void *device_ptr, size_t n_bytes);
+void *yb_stream(yb_ctx *ctx); /* the context's cudaStream_t */
+void *yb_device_classes(yb_ctx *ctx, size_t *n);
+void *yb_device_gap_ptr(yb_ctx *ctx, size_t *n);
+void *yb_device_gaps(yb_ctx *ctx, size_t *n_pairs_capacity);
+int yb_get_stats(yb_ctx *ctx, yb_stats *out);
+
+/* ---- synthetic workload generator (BASELINE.json configs). Host only. ---------- */
+typedef struct yb_synth_spec {
+    uint64_t seed;          /* 20261017 */
+    uint32_t n_reads;       /* GLOBAL number of reads of the workload */
+    uint32_t shard;         /* this shard: reads with yb_synth_shard_of(read, n_shards) == shard */
+    uint32_t n_shards;      /* 0 or 1: no sharding */
+    uint32_t profile;       /* YB_SYNTH_* */
+    double mean_intervals;  /* per read (ignored by the skewed profile) */
+} yb_synth_spec;
+#define YB_SYNTH_ONT 0u          /* ONT lengths, over-dispersed interval counts */
+#define YB_SYNTH_PACBIO_SKEW 1u  /* PacBio Sequel lengths, Pareto interval counts capped at 5000 */
+uint32_t yb_synth_shard_of(uint32_t read, uint32_t n_shards); /* read-id hash sharding */
+uint32_t yb_synth_count(const yb_synth_spec *spec);           /* reads in this shard */
+/* Pass 1: global_idx[0..n_local) (may be NULL), rowptr[0..n_local] and length[0..n_local)
+ * (caller-allocated, n_local = yb_synth_count). Returns the shard's total intervals. */
+uint64_t yb_synth_plan(const yb_synth_spec *spec, uint32_t *global_idx, uint32_t *rowptr,
+                       uint32_t *length);
+/* Pass 2: fill iv (pairs) for the rows planned by pass 1. threads <= 0: all cores. */
+int yb_synth_fill(const yb_synth_spec *spec, const uint32_t *global_idx, const uint32_t *rowptr,
+                  const uint32_t *length, uint32_t n_local, uint32_t *iv, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YACRD_B200_H */

@@ -1,0 +1,986 @@
+// engine.cu — the C ABI (include/yacrd_b200.h): host-side mirror of the reference's Reads2Ovl producer
+// (src/reads2ovl/mod.rs:43-163, FullMemory semantics src/reads2ovl/fullmemory.rs:46-90) and BadPart
+// consumer (src/stack.rs:35-41,143-173), with the device boundary placed where the reference calls
+// get_overlaps (stack.rs:149): host store -> CSR -> HBM -> sm_100a kernels (pileup.cu) -> classes and
+// bad-region CSR back to the host. No CPU implementation of the pile-up exists in this library: without a
+// CUDA device yb_create fails.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/yacrd_b200.h"
+#include "pileup.cuh"
+#include "store.hpp"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+const char *const kTypeNames[3] = {"NotBad", "Chimeric", "NotCovered"};  // editor/mod.rs:51-58
+
+template <typename T>
+struct PinnedBuf {  // page-locked host buffer, grown geometrically
+    T *p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        release();
+        size_t want = n + n / 8 + 16;
+        if (cudaMallocHost(reinterpret_cast<void **>(&p), want * sizeof(T)) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            cap = 0;
+            return false;
+        }
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T>
+struct DeviceBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        release();
+        size_t want = n + n / 16 + 64;
+        if (cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T)) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            cap = 0;
+            return false;
+        }
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+inline char *put_u64(char *p, uint64_t v) {
+    char tmp[24];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+}  // namespace
+
+struct yb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t read_buffer_size = 8192;
+    uint32_t flags = 0;
+    std::string error;
+
+    // ---- host store (Reads2Ovl producer side) ----
+    yb::IdTable ids;                       // named mode: id -> dense first-seen index
+    std::vector<uint64_t> length;          // per read (usize in the reference)
+    std::vector<yb::PendingRecord> pending;  // arrival-order intervals not yet frozen
+    bool indexed = false;                  // reads are named by their decimal index (bulk CSR input)
+    uint32_t n_indexed = 0;
+    // borrowed CSR (yb_bind_csr): caller-owned host buffers used in place
+    const uint32_t *b_rowptr = nullptr, *b_iv = nullptr, *b_len = nullptr;
+
+    // ---- frozen CSR (pinned host) ----
+    PinnedBuf<uint32_t> h_rowptr, h_len;
+    PinnedBuf<uint2> h_iv;
+    std::vector<uint32_t> arrival_rowptr;  // KEEP_HOST_INTERVALS
+    uint32_t n_reads = 0, n_iv = 0, max_k = 0;
+    uint64_t huge_keys = 0;
+    bool frozen = false, uploaded = false, computed = false, downloaded = false, from_report = false;
+
+    // ---- device ----
+    DeviceBuf<uint32_t> d_rowptr, d_len, d_gap_ptr, d_counters;
+    DeviceBuf<uint2> d_iv, d_gaps;
+    DeviceBuf<uint8_t> d_cls, d_bitmap, d_scratch;
+    uint8_t *ext_bitmap = nullptr;  // yb_bind_device_bitmap
+    size_t ext_bitmap_bytes = 0;
+
+    // ---- results (pinned host) ----
+    PinnedBuf<uint8_t> h_cls, h_bitmap;
+    PinnedBuf<uint32_t> h_gap_ptr, h_counters;
+    PinnedBuf<uint2> h_gaps;
+    uint32_t n_gaps = 0;
+    double not_coverage = 0.8;
+    uint64_t coverage = 0;
+
+    yb_stats stats{};
+    std::string scratch_id;  // yb_read_at in indexed mode
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        error = buf;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char *what) {
+        cudaGetLastError();
+        return fail(YB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    size_t bitmap_bytes() const { return (((size_t)n_reads + 15) / 16) * 4; }
+    uint32_t total_reads() const { return indexed ? n_indexed : ids.size(); }
+    void invalidate() { frozen = uploaded = computed = downloaded = false; }
+    const uint32_t *rowptr_host() const { return b_rowptr ? b_rowptr : h_rowptr.p; }
+    const uint32_t *len_host() const { return b_len ? b_len : h_len.p; }
+    const uint2 *iv_host() const { return b_iv ? reinterpret_cast<const uint2 *>(b_iv) : h_iv.p; }
+};
+
+namespace {
+
+#define YB_CUDA(ctx, call)                                   \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return (ctx)->cuda_fail(e_, #call); \
+    } while (0)
+
+bool parse_index_name(const char *id, size_t n, uint64_t *out) {
+    if (n == 0 || n > 10) return false;
+    uint64_t v = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const unsigned d = (unsigned)(id[i] - '0');
+        if (d > 9) return false;
+        v = v * 10 + d;
+    }
+    if (n > 1 && id[0] == '0') return false;
+    *out = v;
+    return true;
+}
+
+int64_t find_read(const yb_ctx *c, const char *id, size_t n) {
+    if (c->indexed) {
+        uint64_t v;
+        if (!parse_index_name(id, n, &v) || v >= c->n_indexed) return -1;
+        return (int64_t)v;
+    }
+    const uint32_t i = c->ids.find(id, n);
+    return i == yb::IdTable::kNone ? -1 : (int64_t)i;
+}
+
+int intern_read(yb_ctx *c, const char *id, size_t n, bool *is_new, uint32_t *idx) {
+    if (c->indexed || c->from_report)
+        return c->fail(YB_ERR_STATE, "this context holds bulk/report input; per-record adds are not allowed");
+    if (c->ids.size() == 0xFFFFFFFEu) return c->fail(YB_ERR_TOO_LARGE, "too many reads");
+    *idx = c->ids.intern(id, n, is_new);
+    if (*is_new) c->length.push_back(0);
+    return YB_OK;
+}
+
+// Freeze: counting sort of the arrival-order records by read -> CSR in pinned memory. Within a read the
+// arrival order is kept (the kernels sort anyway; yb_overlap shows arrival order like Reads2Ovl::overlap).
+int freeze(yb_ctx *c) {
+    if (c->frozen) return YB_OK;
+    if (c->b_rowptr) {  // borrowed CSR: only derive the row statistics
+        const uint32_t n = c->n_indexed;
+        uint32_t mk = 0;
+        uint64_t huge = 0;
+        for (uint32_t r = 0; r < n; ++r) {
+            if (c->b_rowptr[r + 1] < c->b_rowptr[r]) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr is not monotone at read %u", r);
+            if (c->b_len[r] > yb::kMaxLength) return c->fail(YB_ERR_TOO_LARGE, "read %u is longer than 2^31-1 bases", r);
+            const uint32_t k = c->b_rowptr[r + 1] - c->b_rowptr[r];
+            mk = std::max(mk, k);
+            huge += yb::huge_keys_for_row(k);
+        }
+        c->n_reads = n;
+        c->n_iv = n ? c->b_rowptr[n] - c->b_rowptr[0] : 0;
+        if (n && c->b_rowptr[0] != 0) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr[0] must be 0");
+        c->max_k = mk;
+        c->huge_keys = huge;
+        c->frozen = true;
+        return YB_OK;
+    }
+    const uint32_t n = c->ids.size();
+    const size_t m = c->pending.size();
+    if (m > 0xFFFFFFF0ull) return c->fail(YB_ERR_TOO_LARGE, "more than 2^32-16 intervals in one context");
+    if (!c->h_rowptr.reserve((size_t)n + 1) || !c->h_len.reserve((size_t)n + 1) || !c->h_iv.reserve(m + 1))
+        return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
+    uint32_t *rp = c->h_rowptr.p;
+    memset(rp, 0, sizeof(uint32_t) * ((size_t)n + 1));
+    for (size_t i = 0; i < m; ++i) rp[c->pending[i].read + 1]++;
+    uint32_t mk = 0;
+    uint64_t huge = 0;
+    for (uint32_t r = 0; r < n; ++r) {
+        mk = std::max(mk, rp[r + 1]);
+        huge += yb::huge_keys_for_row(rp[r + 1]);
+        rp[r + 1] += rp[r];
+    }
+    std::vector<uint32_t> cur(rp, rp + n);
+    for (size_t i = 0; i < m; ++i) {
+        const yb::PendingRecord &p = c->pending[i];
+        c->h_iv.p[cur[p.read]++] = make_uint2(p.begin, p.end);
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        if (c->length[r] > yb::kMaxLength)
+            return c->fail(YB_ERR_TOO_LARGE, "read %u is longer than 2^31-1 bases", r);
+        c->h_len.p[r] = (uint32_t)c->length[r];
+    }
+    c->n_reads = n;
+    c->n_iv = (uint32_t)m;
+    c->max_k = mk;
+    c->huge_keys = huge;
+    c->frozen = true;
+    return YB_OK;
+}
+
+int ensure_result_buffers(yb_ctx *c) {
+    const size_t n = c->n_reads;
+    if (!c->d_cls.reserve(n + 16) || !c->d_gap_ptr.reserve(n + 1) || !c->d_bitmap.reserve(c->bitmap_bytes() + 4) ||
+        !c->d_counters.reserve(yb::kNumCounters) || !c->d_gaps.reserve((size_t)c->n_iv + n + 1))
+        return c->fail(YB_ERR_NOMEM, "device allocation failed (%zu reads, %u intervals)", n, c->n_iv);
+    return YB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *yb_version(void) { return YB_VERSION; }
+const char *yb_type_name(int t) { return (t >= 0 && t < 3) ? kTypeNames[t] : "?"; }
+const char *yb_create_error(void) { return g_create_error.c_str(); }
+const char *yb_last_error(const yb_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+yb_ctx *yb_create(const yb_opts *opts) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no usable CUDA device (the detect path has no CPU fallback): ") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return nullptr;
+    }
+    yb_ctx *c = new (std::nothrow) yb_ctx();
+    if (!c) {
+        g_create_error = "out of memory";
+        return nullptr;
+    }
+    int dev = opts ? opts->device : -1;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    }
+    if (dev >= count || cudaSetDevice(dev) != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = "invalid CUDA device ordinal " + std::to_string(dev);
+        delete c;
+        return nullptr;
+    }
+    c->device = dev;
+    if (opts) {
+        if (opts->read_buffer_size) c->read_buffer_size = opts->read_buffer_size;
+        c->flags = opts->flags;
+    }
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void yb_destroy(yb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    c->h_rowptr.release();
+    c->h_len.release();
+    c->h_iv.release();
+    c->h_cls.release();
+    c->h_bitmap.release();
+    c->h_gap_ptr.release();
+    c->h_counters.release();
+    c->h_gaps.release();
+    c->d_rowptr.release();
+    c->d_len.release();
+    c->d_gap_ptr.release();
+    c->d_counters.release();
+    c->d_iv.release();
+    c->d_gaps.release();
+    c->d_cls.release();
+    c->d_bitmap.release();
+    c->d_scratch.release();
+    delete c;
+}
+
+// Page-locked when a CUDA driver is present; otherwise (CPU-only box: tests of the generator and of the
+// host logic) plain aligned memory, remembered so that yb_host_free releases it the right way.
+static std::mutex g_host_mu;
+static std::unordered_set<void *> g_host_plain;
+
+// Drop the store and the results but keep every host/device allocation: the next get_overlaps batch
+// (stack.rs:148-161 loops over batches) reuses them.
+int yb_reset(yb_ctx *c) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->ids.clear();
+    c->length.clear();
+    c->pending.clear();
+    c->indexed = false;
+    c->n_indexed = 0;
+    c->b_rowptr = c->b_iv = c->b_len = nullptr;
+    c->n_reads = c->n_iv = c->max_k = c->n_gaps = 0;
+    c->huge_keys = 0;
+    c->from_report = false;
+    c->invalidate();
+    return YB_OK;
+}
+
+void *yb_host_alloc(size_t n_bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, n_bytes ? n_bytes : 1) == cudaSuccess) return p;
+    cudaGetLastError();
+    p = aligned_alloc(256, ((n_bytes ? n_bytes : 1) + 255) & ~(size_t)255);
+    if (p) {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        g_host_plain.insert(p);
+    }
+    return p;
+}
+void yb_host_free(void *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        auto it = g_host_plain.find(p);
+        if (it != g_host_plain.end()) {
+            g_host_plain.erase(it);
+            free(p);
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
+
+// ---- producer side ---------------------------------------------------------------------------------
+int yb_add_overlap_and_length(yb_ctx *c, const char *id, size_t id_len, uint32_t begin, uint32_t end,
+                              uint64_t length) {
+    if (!c || (!id && id_len)) return YB_ERR_INVALID_ARGUMENT;
+    bool is_new = false;
+    uint32_t idx = 0;
+    if (int rc = intern_read(c, id, id_len, &is_new, &idx)) return rc;
+    if (is_new) c->length[idx] = length;  // fullmemory.rs:82-90: first-seen length wins
+    c->pending.push_back({idx, begin, end});
+    c->invalidate();
+    return YB_OK;
+}
+
+int yb_add_overlap(yb_ctx *c, const char *id, size_t id_len, uint32_t begin, uint32_t end) {
+    if (!c || (!id && id_len)) return YB_ERR_INVALID_ARGUMENT;
+    bool is_new = false;
+    uint32_t idx = 0;
+    if (int rc = intern_read(c, id, id_len, &is_new, &idx)) return rc;  // fullmemory.rs:68-76: length 0
+    c->pending.push_back({idx, begin, end});
+    c->invalidate();
+    return YB_OK;
+}
+
+int yb_add_length(yb_ctx *c, const char *id, size_t id_len, uint64_t length) {
+    if (!c || (!id && id_len)) return YB_ERR_INVALID_ARGUMENT;
+    bool is_new = false;
+    uint32_t idx = 0;
+    if (int rc = intern_read(c, id, id_len, &is_new, &idx)) return rc;
+    c->length[idx] = length;  // fullmemory.rs:78-80: sets unconditionally
+    c->invalidate();
+    return YB_OK;
+}
+
+int yb_add_csr(yb_ctx *c, const uint32_t *rowptr, const uint32_t *iv, const uint32_t *length, uint32_t n_reads,
+               const char *const *ids, const size_t *id_lens) {
+    if (!c || !rowptr || !length || (!iv && n_reads && rowptr[n_reads] != rowptr[0]))
+        return YB_ERR_INVALID_ARGUMENT;
+    if (c->from_report || c->b_rowptr) return c->fail(YB_ERR_STATE, "context already holds report/borrowed input");
+    if (!ids) {
+        // index-named bulk input: copy straight into the pinned CSR (appending)
+        if (c->ids.size()) return c->fail(YB_ERR_STATE, "index-named bulk input cannot follow named reads");
+        const uint32_t old_n = c->n_indexed;
+        const uint64_t old_m = old_n ? c->h_rowptr.p[old_n] : 0;
+        const uint64_t add_m = (uint64_t)rowptr[n_reads] - rowptr[0];
+        if (old_m + add_m > 0xFFFFFFF0ull || (uint64_t)old_n + n_reads > 0xFFFFFFF0ull)
+            return c->fail(YB_ERR_TOO_LARGE, "more than 2^32-16 intervals or reads in one context");
+        PinnedBuf<uint32_t> nr, nl;
+        PinnedBuf<uint2> ni;
+        const size_t tn = (size_t)old_n + n_reads;
+        if (tn + 1 > c->h_rowptr.cap || old_m + add_m + 1 > c->h_iv.cap) {
+            if (!nr.reserve(tn + 1) || !nl.reserve(tn + 1) || !ni.reserve(old_m + add_m + 1))
+                return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
+            if (old_n) {
+                memcpy(nr.p, c->h_rowptr.p, sizeof(uint32_t) * ((size_t)old_n + 1));
+                memcpy(nl.p, c->h_len.p, sizeof(uint32_t) * old_n);
+                memcpy(ni.p, c->h_iv.p, sizeof(uint2) * old_m);
+            } else {
+                nr.p[0] = 0;
+            }
+            c->h_rowptr.release();
+            c->h_len.release();
+            c->h_iv.release();
+            c->h_rowptr = nr;
+            c->h_len = nl;
+            c->h_iv = ni;
+        } else if (!old_n) {
+            c->h_rowptr.p[0] = 0;
+        }
+        uint32_t mk = old_n ? c->max_k : 0;
+        uint64_t huge = old_n ? c->huge_keys : 0;
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            if (rowptr[r + 1] < rowptr[r]) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr is not monotone at read %u", r);
+            if (length[r] > yb::kMaxLength) return c->fail(YB_ERR_TOO_LARGE, "read %u is longer than 2^31-1 bases", r);
+            const uint32_t k = rowptr[r + 1] - rowptr[r];
+            mk = std::max(mk, k);
+            huge += yb::huge_keys_for_row(k);
+            c->h_rowptr.p[old_n + r + 1] = (uint32_t)(old_m + (rowptr[r + 1] - rowptr[0]));
+            c->h_len.p[old_n + r] = length[r];
+        }
+        if (add_m) memcpy(c->h_iv.p + old_m, iv + 2 * (size_t)rowptr[0], sizeof(uint2) * add_m);
+        c->indexed = true;
+        c->n_indexed = (uint32_t)tn;
+        c->n_reads = (uint32_t)tn;
+        c->n_iv = (uint32_t)(old_m + add_m);
+        c->max_k = mk;
+        c->huge_keys = huge;
+        c->invalidate();
+        c->frozen = true;
+        return YB_OK;
+    }
+    if (c->indexed) return c->fail(YB_ERR_STATE, "named reads cannot follow index-named bulk input");
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        const size_t idl = id_lens ? id_lens[r] : strlen(ids[r]);
+        bool is_new;
+        uint32_t idx;
+        if (int rc = intern_read(c, ids[r], idl, &is_new, &idx)) return rc;
+        if (is_new) c->length[idx] = length[r];
+        for (uint32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) c->pending.push_back({idx, iv[2 * (size_t)j], iv[2 * (size_t)j + 1]});
+    }
+    c->invalidate();
+    return YB_OK;
+}
+
+int yb_bind_csr(yb_ctx *c, const uint32_t *rowptr, const uint32_t *iv, const uint32_t *length, uint32_t n_reads) {
+    if (!c || !rowptr || !length || (!iv && n_reads && rowptr[n_reads])) return YB_ERR_INVALID_ARGUMENT;
+    if (c->ids.size() || c->from_report || (c->indexed && !c->b_rowptr))
+        return c->fail(YB_ERR_STATE, "yb_bind_csr needs an empty context");
+    c->b_rowptr = rowptr;
+    c->b_iv = iv;
+    c->b_len = length;
+    c->indexed = true;
+    c->n_indexed = n_reads;
+    c->invalidate();
+    return YB_OK;
+}
+
+static bool add_sink(void *sink, const char *id, size_t id_len, uint32_t b, uint32_t e, uint64_t len) {
+    return yb_add_overlap_and_length(static_cast<yb_ctx *>(sink), id, id_len, b, e, len) == YB_OK;
+}
+
+int yb_init_buffer(yb_ctx *c, const char *text, size_t n_bytes, int format) {
+    if (!c || (!text && n_bytes) || (format != 'p' && format != 'm')) return YB_ERR_INVALID_ARGUMENT;
+    yb::IngestError err;
+    if (!yb::ingest_buffer(text, n_bytes, format, add_sink, c, &err)) {
+        if (err.code == YB_ERR_NOMEM && !c->error.empty()) return YB_ERR_STATE;  // add refused (state)
+        return c->fail(err.code, "%s", err.message.c_str());
+    }
+    return YB_OK;
+}
+
+int yb_file_type(const char *path) {  // util.rs:39-55, same precedence
+    if (!path) return 0;
+    const std::string f(path);
+    auto has = [&](const char *s) { return f.find(s) != std::string::npos; };
+    if (has(".m4") || has(".mhap")) return 'm';
+    if (has(".paf")) return 'p';
+    if (has(".yacrd")) return 'y';
+    if (has(".fastq") || has(".fq")) return 'q';
+    if (has(".fasta") || has(".fa")) return 'a';
+    if (has(".yovl")) return 'o';
+    return 0;
+}
+
+static int slurp(yb_ctx *c, const char *path, std::vector<char> *out) {
+    FILE *fh = fopen(path, "rb");
+    if (!fh) return c->fail(YB_ERR_CANT_READ_FILE, "Can't open file %s: %s", path, strerror(errno));
+    std::vector<char> buf((size_t)c->read_buffer_size > 65536 ? c->read_buffer_size : 65536);
+    size_t got;
+    while ((got = fread(buf.data(), 1, buf.size(), fh)) > 0) out->insert(out->end(), buf.data(), buf.data() + got);
+    const bool bad = ferror(fh);
+    fclose(fh);
+    if (bad) return c->fail(YB_ERR_CANT_READ_FILE, "Error while reading %s", path);
+    return YB_OK;
+}
+
+int yb_init_file(yb_ctx *c, const char *path) {
+    if (!c || !path) return YB_ERR_INVALID_ARGUMENT;
+    const int t = yb_file_type(path);  // reads2ovl/mod.rs:51-79
+    if (t == 0 || t == 'o') return c->fail(YB_ERR_UNKNOWN_FORMAT, "Format detection for '%s' file not possible", path);
+    if (t != 'p' && t != 'm')
+        return c->fail(YB_ERR_WRONG_FORMAT, "Can't run overlap parsing on %s file %s",
+                       t == 'y' ? "yacrd" : (t == 'q' ? "fastq" : "fasta"), path);
+    std::vector<char> text;
+    if (int rc = slurp(c, path, &text)) return rc;
+    if (text.size() >= 2 && (unsigned char)text[0] == 0x1f && (unsigned char)text[1] == 0x8b)
+        return c->fail(YB_ERR_CANT_READ_FILE, "%s is gzip-compressed; decompress it first (compressed input is out of scope)", path);
+    const int rc = yb_init_buffer(c, text.data(), text.size(), t);
+    if (rc != YB_OK) c->error += std::string(" (Filename: ") + path + ")";
+    return rc;
+}
+
+uint64_t yb_length(const yb_ctx *c, const char *id, size_t id_len) {
+    if (!c) return 0;
+    const int64_t i = find_read(c, id, id_len);
+    if (i < 0) return 0;
+    if (c->indexed) return c->frozen || c->b_len ? c->len_host()[i] : 0;
+    return c->length[(size_t)i];
+}
+
+uint32_t yb_n_reads(const yb_ctx *c) { return c ? c->total_reads() : 0; }
+
+int yb_read_at(const yb_ctx *cc, uint32_t idx, const char **id, size_t *id_len) {
+    yb_ctx *c = const_cast<yb_ctx *>(cc);
+    if (!c || !id || !id_len) return YB_ERR_INVALID_ARGUMENT;
+    if (idx >= c->total_reads()) return c->fail(YB_ERR_INVALID_ARGUMENT, "read index %u out of range", idx);
+    if (c->indexed) {
+        c->scratch_id = std::to_string(idx);
+        *id = c->scratch_id.data();
+        *id_len = c->scratch_id.size();
+    } else {
+        *id = c->ids.id(idx, id_len);
+    }
+    return YB_OK;
+}
+
+int64_t yb_read_index(const yb_ctx *c, const char *id, size_t id_len) { return c ? find_read(c, id, id_len) : -1; }
+
+int yb_overlap(yb_ctx *c, const char *id, size_t id_len, const uint32_t **iv_pairs, uint32_t *n_intervals) {
+    if (!c || !iv_pairs || !n_intervals) return YB_ERR_INVALID_ARGUMENT;
+    *iv_pairs = nullptr;
+    *n_intervals = 0;
+    const int64_t i = find_read(c, id, id_len);
+    if (i < 0) return YB_OK;  // fullmemory.rs:52-58: unknown read => empty
+    if (c->from_report) return YB_OK;
+    if (int rc = freeze(c)) return rc;
+    const uint32_t *rp = c->rowptr_host();
+    *iv_pairs = reinterpret_cast<const uint32_t *>(c->iv_host() + rp[i]);
+    *n_intervals = rp[i + 1] - rp[i];
+    return YB_OK;
+}
+
+// ---- staged device API -------------------------------------------------------------------------------
+int yb_upload(yb_ctx *c) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (c->from_report) return c->fail(YB_ERR_STATE, "context was loaded from a report; nothing to upload");
+    YB_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = freeze(c)) return rc;
+    if (c->uploaded) return YB_OK;
+    const size_t n = c->n_reads, m = c->n_iv;
+    if (!c->d_rowptr.reserve(n + 1) || !c->d_len.reserve(n + 1) || !c->d_iv.reserve(m + 2))
+        return c->fail(YB_ERR_NOMEM, "device allocation failed (%zu reads, %zu intervals)", n, m);
+    if (int rc = ensure_result_buffers(c)) return rc;
+    const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->max_k, c->huge_keys);
+    if (!c->d_scratch.reserve(sb)) return c->fail(YB_ERR_NOMEM, "device scratch allocation failed (%zu bytes)", sb);
+    if (n) {
+        YB_CUDA(c, cudaMemcpyAsync(c->d_rowptr.p, c->rowptr_host(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+        YB_CUDA(c, cudaMemcpyAsync(c->d_len.p, c->len_host(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        if (m) YB_CUDA(c, cudaMemcpyAsync(c->d_iv.p, c->iv_host(), sizeof(uint2) * m, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->stats.h2d_bytes += sizeof(uint32_t) * (2 * n + 1) + sizeof(uint2) * m;
+    c->uploaded = true;
+    c->computed = c->downloaded = false;
+    return YB_OK;
+}
+
+int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *stream) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    YB_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    c->coverage = coverage;
+    c->not_coverage = not_coverage;
+    int launches;
+    if (c->from_report) {
+        launches = yb::launch_classify(c->d_len.p, c->d_gap_ptr.p, c->d_gaps.p, c->n_reads, not_coverage, c->d_cls.p,
+                                       c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p, c->d_counters.p, st);
+    } else {
+        if (!c->uploaded) return c->fail(YB_ERR_STATE, "yb_compute_device before yb_upload");
+        yb::DetectArgs a{};
+        a.iv = c->d_iv.p;
+        a.rowptr = c->d_rowptr.p;
+        a.len = c->d_len.p;
+        a.n_reads = c->n_reads;
+        a.n_iv = c->n_iv;
+        a.max_k = c->max_k;
+        a.cls = c->d_cls.p;
+        a.gap_ptr = c->d_gap_ptr.p;
+        a.gaps = c->d_gaps.p;
+        a.bitmap = c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p;
+        a.counters = c->d_counters.p;
+        a.scratch = c->d_scratch.p;
+        a.scratch_bytes = c->d_scratch.cap;
+        if (c->ext_bitmap && c->ext_bitmap_bytes < c->bitmap_bytes())
+            return c->fail(YB_ERR_INVALID_ARGUMENT, "bound bitmap buffer too small (%zu < %zu bytes)", c->ext_bitmap_bytes, c->bitmap_bytes());
+        launches = yb::launch_detect(a, coverage > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)coverage, not_coverage, st);
+    }
+    if (launches < 0) return c->cuda_fail(cudaGetLastError(), "kernel launch");
+    c->stats.kernel_launches += (uint64_t)launches;
+    c->computed = true;
+    c->downloaded = false;
+    return YB_OK;
+}
+
+int yb_synchronize(yb_ctx *c) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    YB_CUDA(c, cudaSetDevice(c->device));
+    YB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return YB_OK;
+}
+
+int yb_download(yb_ctx *c) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->computed) return c->fail(YB_ERR_STATE, "yb_download before yb_compute_device");
+    if (c->downloaded) return YB_OK;
+    YB_CUDA(c, cudaSetDevice(c->device));
+    const size_t n = c->n_reads;
+    if (!c->h_cls.reserve(n + 1) || !c->h_gap_ptr.reserve(n + 1) || !c->h_bitmap.reserve(c->bitmap_bytes() + 4) ||
+        !c->h_counters.reserve(yb::kNumCounters))
+        return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
+    YB_CUDA(c, cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, sizeof(uint32_t) * yb::kNumCounters, cudaMemcpyDeviceToHost, c->stream));
+    YB_CUDA(c, cudaMemcpyAsync(c->h_gap_ptr.p, c->d_gap_ptr.p, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (n) {
+        YB_CUDA(c, cudaMemcpyAsync(c->h_cls.p, c->d_cls.p, n, cudaMemcpyDeviceToHost, c->stream));
+        YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p, c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p, c->bitmap_bytes(), cudaMemcpyDeviceToHost, c->stream));
+    }
+    YB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->h_counters.p[yb::kCntMalformed])
+        return c->fail(YB_ERR_MALFORMED_INTERVAL,
+                       "%u interval(s) violate 0 <= begin < end <= length; the reference's result is undefined for them",
+                       c->h_counters.p[yb::kCntMalformed]);
+    c->n_gaps = c->h_gap_ptr.p[n];
+    size_t d2h = sizeof(uint32_t) * (n + 1 + yb::kNumCounters) + n + c->bitmap_bytes();
+    if (!c->from_report) {
+        if (!c->h_gaps.reserve((size_t)c->n_gaps + 1)) return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
+        if (c->n_gaps) {
+            YB_CUDA(c, cudaMemcpyAsync(c->h_gaps.p, c->d_gaps.p, sizeof(uint2) * c->n_gaps, cudaMemcpyDeviceToHost, c->stream));
+            YB_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        d2h += sizeof(uint2) * c->n_gaps;
+    }
+    c->stats.d2h_bytes += d2h;
+    c->stats.n_reads = n;
+    c->stats.n_intervals = c->n_iv;
+    c->stats.n_gaps = c->n_gaps;
+    c->stats.n_not_bad = c->h_counters.p[yb::kCntNotBad];
+    c->stats.n_chimeric = c->h_counters.p[yb::kCntChimeric];
+    c->stats.n_not_covered = c->h_counters.p[yb::kCntNotCovered];
+    c->stats.max_intervals_per_read = c->max_k;
+    c->downloaded = true;
+    return YB_OK;
+}
+
+int yb_compute_all_bad_part(yb_ctx *c, uint64_t coverage, double not_coverage) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->from_report)
+        if (int rc = yb_upload(c)) return rc;
+    if (int rc = yb_compute_device(c, coverage, not_coverage, nullptr)) return rc;
+    return yb_download(c);
+}
+
+int yb_bind_device_bitmap(yb_ctx *c, void *device_ptr, size_t n_bytes) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    c->ext_bitmap = static_cast<uint8_t *>(device_ptr);
+    c->ext_bitmap_bytes = device_ptr ? n_bytes : 0;
+    return YB_OK;
+}
+
+void *yb_device_class_bitmap(yb_ctx *c, size_t *n_bytes) {
+    if (!c) return nullptr;
+    if (n_bytes) *n_bytes = c->bitmap_bytes();
+    return c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p;
+}
+void *yb_device_classes(yb_ctx *c, size_t *n) {
+    if (!c) return nullptr;
+    if (n) *n = c->n_reads;
+    return c->d_cls.p;
+}
+void *yb_device_gap_ptr(yb_ctx *c, size_t *n) {
+    if (!c) return nullptr;
+    if (n) *n = (size_t)c->n_reads + 1;
+    return c->d_gap_ptr.p;
+}
+void *yb_device_gaps(yb_ctx *c, size_t *cap) {
+    if (!c) return nullptr;
+    if (cap) *cap = c->d_gaps.cap;
+    return c->d_gaps.p;
+}
+void *yb_stream(yb_ctx *c) { return c ? c->stream : nullptr; }
+
+int yb_get_stats(yb_ctx *c, yb_stats *out) {
+    if (!c || !out) return YB_ERR_INVALID_ARGUMENT;
+    *out = c->stats;
+    return YB_OK;
+}
+
+// ---- consumer side -----------------------------------------------------------------------------------
+int yb_get_bad_part_at(yb_ctx *c, uint32_t idx, const uint32_t **gap_pairs, uint32_t *n_gaps, uint64_t *length,
+                       uint8_t *cls) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->downloaded) return c->fail(YB_ERR_STATE, "results queried before yb_compute_all_bad_part / yb_download");
+    if (idx >= c->n_reads) return c->fail(YB_ERR_INVALID_ARGUMENT, "read index %u out of range", idx);
+    const uint32_t g0 = c->h_gap_ptr.p[idx], g1 = c->h_gap_ptr.p[idx + 1];
+    if (gap_pairs) *gap_pairs = reinterpret_cast<const uint32_t *>(c->h_gaps.p + g0);
+    if (n_gaps) *n_gaps = g1 - g0;
+    if (length) *length = c->from_report ? c->length[idx] : c->len_host()[idx];
+    if (cls) *cls = c->h_cls.p[idx];
+    return YB_OK;
+}
+
+int yb_get_bad_part(yb_ctx *c, const char *id, size_t id_len, const uint32_t **gap_pairs, uint32_t *n_gaps,
+                    uint64_t *length, uint8_t *cls) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->downloaded) return c->fail(YB_ERR_STATE, "results queried before yb_compute_all_bad_part / yb_download");
+    const int64_t i = find_read(c, id, id_len);
+    if (i < 0) {  // stack.rs:164-169: unknown id => (vec![], 0); 0/0 = NaN is not > n => NotBad
+        if (gap_pairs) *gap_pairs = nullptr;
+        if (n_gaps) *n_gaps = 0;
+        if (length) *length = 0;
+        if (cls) *cls = YB_NOT_BAD;
+        return YB_OK;
+    }
+    return yb_get_bad_part_at(c, (uint32_t)i, gap_pairs, n_gaps, length, cls);
+}
+
+const uint8_t *yb_classes(yb_ctx *c, size_t *n) {
+    if (!c || !c->downloaded) return nullptr;
+    if (n) *n = c->n_reads;
+    return c->h_cls.p;
+}
+const uint8_t *yb_class_bitmap(yb_ctx *c, size_t *n_bytes) {
+    if (!c || !c->downloaded) return nullptr;
+    if (n_bytes) *n_bytes = c->bitmap_bytes();
+    return c->h_bitmap.p;
+}
+const uint32_t *yb_gap_ptr(yb_ctx *c, size_t *n) {
+    if (!c || !c->downloaded) return nullptr;
+    if (n) *n = (size_t)c->n_reads + 1;
+    return c->h_gap_ptr.p;
+}
+const uint32_t *yb_gaps(yb_ctx *c, size_t *n_pairs) {
+    if (!c || !c->downloaded) return nullptr;
+    if (n_pairs) *n_pairs = c->n_gaps;
+    return reinterpret_cast<const uint32_t *>(c->h_gaps.p);
+}
+
+// editor/mod.rs:72-79,102-107: "{type}\t{id}\t{len}\t{len,beg,end;...}"
+static size_t format_line(yb_ctx *c, uint32_t idx, std::vector<char> *buf) {
+    const char *id;
+    size_t idl;
+    std::string tmp;
+    if (c->indexed) {
+        tmp = std::to_string(idx);
+        id = tmp.data();
+        idl = tmp.size();
+    } else {
+        id = c->ids.id(idx, &idl);
+    }
+    const uint32_t g0 = c->h_gap_ptr.p[idx], g1 = c->h_gap_ptr.p[idx + 1];
+    const size_t need = 16 + idl + 24 + (size_t)(g1 - g0) * 34 + 2;
+    const size_t at = buf->size();
+    buf->resize(at + need);
+    char *p = buf->data() + at;
+    const char *t = kTypeNames[c->h_cls.p[idx] < 3 ? c->h_cls.p[idx] : 0];
+    const size_t tl = strlen(t);
+    memcpy(p, t, tl);
+    p += tl;
+    *p++ = '\t';
+    memcpy(p, id, idl);
+    p += idl;
+    *p++ = '\t';
+    p = put_u64(p, c->from_report ? c->length[idx] : c->len_host()[idx]);
+    *p++ = '\t';
+    for (uint32_t g = g0; g < g1; ++g) {
+        const uint2 v = c->h_gaps.p[g];
+        if (g != g0) *p++ = ';';
+        p = put_u64(p, (uint32_t)(v.y - v.x));
+        *p++ = ',';
+        p = put_u64(p, v.x);
+        *p++ = ',';
+        p = put_u64(p, v.y);
+    }
+    const size_t used = (size_t)(p - (buf->data() + at));
+    buf->resize(at + used);
+    return used;
+}
+
+int64_t yb_format_report_line(yb_ctx *c, uint32_t idx, char *out, size_t cap) {
+    if (!c || !out) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->downloaded) return c->fail(YB_ERR_STATE, "results queried before compute");
+    if (idx >= c->n_reads) return c->fail(YB_ERR_INVALID_ARGUMENT, "read index %u out of range", idx);
+    std::vector<char> buf;
+    const size_t n = format_line(c, idx, &buf);
+    if (n + 1 > cap) return c->fail(YB_ERR_INVALID_ARGUMENT, "line needs %zu bytes", n + 1);
+    memcpy(out, buf.data(), n);
+    out[n] = 0;
+    return (int64_t)n;
+}
+
+int yb_write_report(yb_ctx *c, const char *path) {  // main.rs:62-84
+    if (!c || !path) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->downloaded) return c->fail(YB_ERR_STATE, "yb_write_report before yb_compute_all_bad_part");
+    FILE *fh = fopen(path, "wb");
+    if (!fh) return c->fail(YB_ERR_CANT_WRITE_FILE, "Can't create file %s: %s", path, strerror(errno));
+    std::vector<char> buf;
+    buf.reserve(1 << 22);
+    bool ok = true;
+    for (uint32_t r = 0; r < c->n_reads && ok; ++r) {
+        format_line(c, r, &buf);
+        buf.push_back('\n');
+        if (buf.size() > (1u << 22) - 4096) {
+            ok = fwrite(buf.data(), 1, buf.size(), fh) == buf.size();
+            buf.clear();
+        }
+    }
+    if (ok && !buf.empty()) ok = fwrite(buf.data(), 1, buf.size(), fh) == buf.size();
+    if (fclose(fh) != 0) ok = false;
+    if (!ok) return c->fail(YB_ERR_WRITING, "Error during writing of file in yacrd format (%s)", path);
+    return YB_OK;
+}
+
+// ---- FromReport (stack.rs:176-257) -------------------------------------------------------------------
+int yb_init_report_buffer(yb_ctx *c, const char *text, size_t n_bytes) {
+    if (!c || (!text && n_bytes)) return YB_ERR_INVALID_ARGUMENT;
+    if (c->total_reads() || c->from_report) return c->fail(YB_ERR_STATE, "yb_init_report needs an empty context");
+    YB_CUDA(c, cudaSetDevice(c->device));
+    std::vector<uint32_t> gp(1, 0);
+    std::vector<uint2> gaps;
+    std::vector<uint32_t> slot_gp_begin;  // per read index: where its gaps start (last occurrence wins)
+    struct Row { uint64_t len; uint32_t g0, g1; };
+    std::vector<Row> rows;
+    const char *p = text, *const end = text + n_bytes;
+    uint64_t line = 0;
+    auto corrupt = [&](uint64_t ln) { return c->fail(YB_ERR_CORRUPT_REPORT, "Your yacrd file is corrupt at line %llu", (unsigned long long)ln); };
+    auto parse_u = [](const char *s, const char *e, uint64_t max, uint64_t *out) {
+        if (s < e && *s == '+') ++s;
+        if (s == e) return false;
+        uint64_t v = 0;
+        for (; s < e; ++s) {
+            const unsigned d = (unsigned)(*s - '0');
+            if (d > 9 || v > (max - d) / 10) return false;
+            v = v * 10 + d;
+        }
+        *out = v;
+        return true;
+    };
+    while (p < end) {
+        const char *q = p;
+        while (q < end && *q != '\n' && *q != '\r') ++q;
+        const char *le = q;
+        if (q < end) {
+            if (*q == '\r' && q + 1 < end && q[1] == '\n') ++q;
+            ++q;
+        }
+        const char *ls = p;
+        p = q;
+        if (le == ls) continue;
+        // split 4 tab-separated fields: type, id, length, bad string (stack.rs:203-211)
+        const char *f[5];
+        int nf = 0;
+        f[nf++] = ls;
+        for (const char *s = ls; s < le && nf < 4; ++s)
+            if (*s == '\t') f[nf++] = s + 1;
+        if (nf < 4) return corrupt(line);
+        const char *id = f[1], *id_e = f[2] - 1, *len_s = f[2], *len_e = f[3] - 1, *bad = f[3];
+        const char *bad_e = bad;
+        while (bad_e < le && *bad_e != '\t') ++bad_e;
+        uint64_t len;
+        if (!parse_u(len_s, len_e, UINT64_MAX, &len)) return corrupt(line);
+        bool is_new;
+        const uint32_t idx = c->ids.intern(id, (size_t)(id_e - id), &is_new);
+        const uint32_t g0 = (uint32_t)gaps.size();
+        if (bad != bad_e) {  // parse_bad_string, stack.rs:217-241: "len,begin,end" joined by ';'
+            const char *s = bad;
+            while (s <= bad_e) {
+                const char *se = s;
+                while (se < bad_e && *se != ';') ++se;
+                const char *c1 = s;
+                while (c1 < se && *c1 != ',') ++c1;
+                if (c1 == se) return corrupt(line);
+                const char *c2 = c1 + 1;
+                while (c2 < se && *c2 != ',') ++c2;
+                if (c2 == se) return corrupt(line);
+                const char *c3 = c2 + 1;
+                while (c3 < se && *c3 != ',') ++c3;
+                uint64_t b, e;
+                if (!parse_u(c1 + 1, c2, UINT32_MAX, &b) || !parse_u(c2 + 1, c3, UINT32_MAX, &e)) return corrupt(line);
+                gaps.push_back(make_uint2((uint32_t)b, (uint32_t)e));
+                s = se + 1;
+                if (se == bad_e) break;
+            }
+        }
+        const Row row{len, g0, (uint32_t)gaps.size()};
+        if (is_new)
+            rows.push_back(row);
+        else
+            rows[idx] = row;  // HashMap::insert: a repeated id keeps the last line (stack.rs:213)
+        ++line;
+    }
+    // compact rows into a gap CSR in read order
+    const size_t n = rows.size();
+    c->length.resize(n);
+    if (!c->h_gap_ptr.reserve(n + 1) || !c->h_len.reserve(n + 1)) return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
+    size_t tot = 0;
+    for (size_t r = 0; r < n; ++r) tot += rows[r].g1 - rows[r].g0;
+    if (!c->h_gaps.reserve(tot + 1)) return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
+    size_t at = 0;
+    for (size_t r = 0; r < n; ++r) {
+        c->h_gap_ptr.p[r] = (uint32_t)at;
+        for (uint32_t g = rows[r].g0; g < rows[r].g1; ++g) c->h_gaps.p[at++] = gaps[g];
+        c->length[r] = rows[r].len;
+        c->h_len.p[r] = (uint32_t)rows[r].len;  // `length as u32`, editor/mod.rs:95
+    }
+    c->h_gap_ptr.p[n] = (uint32_t)at;
+    c->n_reads = (uint32_t)n;
+    c->n_iv = 0;
+    c->n_gaps = (uint32_t)at;
+    c->from_report = true;
+    if (!c->d_len.reserve(n + 1) || !c->d_gap_ptr.reserve(n + 1) || !c->d_gaps.reserve(at + 1) || !c->d_cls.reserve(n + 16) ||
+        !c->d_bitmap.reserve(c->bitmap_bytes() + 4) || !c->d_counters.reserve(yb::kNumCounters))
+        return c->fail(YB_ERR_NOMEM, "device allocation failed");
+    YB_CUDA(c, cudaMemcpyAsync(c->d_len.p, c->h_len.p, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    YB_CUDA(c, cudaMemcpyAsync(c->d_gap_ptr.p, c->h_gap_ptr.p, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+    if (at) YB_CUDA(c, cudaMemcpyAsync(c->d_gaps.p, c->h_gaps.p, sizeof(uint2) * at, cudaMemcpyHostToDevice, c->stream));
+    YB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return YB_OK;
+}
+
+int yb_init_report(yb_ctx *c, const char *path) {
+    if (!c || !path) return YB_ERR_INVALID_ARGUMENT;
+    std::vector<char> text;
+    if (int rc = slurp(c, path, &text)) return rc;
+    return yb_init_report_buffer(c, text.data(), text.size());
+}
+
+}  // extern "C"

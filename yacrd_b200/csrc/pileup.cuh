@@ -1,0 +1,63 @@
+// pileup.cuh — internal interface between the C-ABI engine (engine.cu) and the sm_100a kernels
+// (pileup.cu). Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace yb {
+
+// A read with k intervals has 2k events (one begin key 2b+1, one end key 2e per interval); a u32
+// event key needs positions < 2^31, which the engine enforces at upload (YB_ERR_TOO_LARGE).
+constexpr uint32_t kMaxLength = 0x7FFFFFFFu;
+
+// Device counters written by one detect step (u32 each).
+enum Counter : uint32_t {
+    kCntNotBad = 0,      // class histogram
+    kCntChimeric = 1,
+    kCntNotCovered = 2,
+    kCntMalformed = 3,   // intervals violating 0 <= begin < end <= length
+    kCntTile = 4,        // dynamic tile scheduler
+    kCntBigList = 5,     // reads deferred to the CTA tier
+    kCntHugeBump = 6,    // bump allocator (in u32 keys) of the global-scratch tier, low word
+    kCntTierWarp = 8,    // reads taken by each tier
+    kCntTierCta = 9,
+    kCntTierHuge = 10,
+    kNumCounters = 16
+};
+
+struct DetectArgs {
+    // CSR input, resident in HBM
+    const uint2 *iv;         // flat (begin,end) buffer, n_iv entries
+    const uint32_t *rowptr;  // n_reads + 1
+    const uint32_t *len;     // n_reads
+    uint32_t n_reads;
+    uint32_t n_iv;
+    uint32_t max_k;          // largest row (host knows it from the row pointers)
+    // outputs, resident in HBM
+    uint8_t *cls;            // n_reads, yb_read_type
+    uint32_t *gap_ptr;       // n_reads + 1: exclusive scan of per-read bad-region counts
+    uint2 *gaps;             // CSR of bad regions, capacity n_iv + n_reads
+    uint8_t *bitmap;         // ceil(n_reads / 4) bytes rounded up to 4, 2 bits per read
+    uint32_t *counters;      // kNumCounters
+    // scratch
+    void *scratch;
+    size_t scratch_bytes;
+};
+
+// Bytes of scratch launch_detect needs for a CSR of this shape.
+size_t detect_scratch_bytes(uint32_t n_reads, uint32_t n_iv, uint32_t max_k, uint64_t huge_keys);
+// Keys (u32) of global scratch one read with k intervals needs when it exceeds the shared-memory tier
+// (0 otherwise). The engine sums this over the rows at freeze time.
+uint64_t huge_keys_for_row(uint64_t k);
+
+// Enqueues one whole detect step on `stream`. Returns the number of kernel launches enqueued, or -1
+// on a launch error.
+int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, cudaStream_t stream);
+
+// Classification only, over an existing bad-region CSR (FromReport path, stack.rs:176-257 +
+// editor/mod.rs:85-100). Returns launches or -1.
+int launch_classify(const uint32_t *len, const uint32_t *gap_ptr, const uint2 *gaps, uint32_t n_reads,
+                    double not_coverage, uint8_t *cls, uint8_t *bitmap, uint32_t *counters,
+                    cudaStream_t stream);
+
+}  // namespace yb

@@ -1,0 +1,118 @@
+// store.hpp — host-side mirror of the reference's `Reads2Ovl` producer surface
+// (src/reads2ovl/mod.rs:43-163) with FullMemory's semantics (src/reads2ovl/fullmemory.rs:46-90),
+// re-designed for a device consumer: instead of FxHashMap<String,(Vec<(u32,u32)>,usize)> it interns
+// read ids to dense first-seen indices and keeps intervals as arrival-order records that are frozen
+// into one CSR (flat (begin,end) buffer + row pointers + lengths) — the layout the kernels stream.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace yb {
+
+// Open-addressing id -> dense index table over a byte arena (ids are copied once, on first sight).
+class IdTable {
+  public:
+    static constexpr uint32_t kNone = 0xFFFFFFFFu;
+    IdTable() { slots_.assign(1024, kNone); }
+    uint32_t size() const { return (uint32_t)(off_.size() - 1); }
+    const char *id(uint32_t i, size_t *len) const {
+        *len = (size_t)(off_[i + 1] - off_[i]);
+        return bytes_.data() + off_[i];
+    }
+    uint32_t find(const char *s, size_t n) const {
+        const uint64_t h = hash(s, n);
+        const size_t mask = slots_.size() - 1;
+        for (size_t p = (size_t)h & mask;; p = (p + 1) & mask) {
+            const uint32_t i = slots_[p];
+            if (i == kNone) return kNone;
+            if (equal(i, s, n)) return i;
+        }
+    }
+    // Returns the index of `s`, inserting it if new (*inserted tells which).
+    uint32_t intern(const char *s, size_t n, bool *inserted) {
+        const uint64_t h = hash(s, n);
+        size_t mask = slots_.size() - 1;
+        size_t p = (size_t)h & mask;
+        for (;; p = (p + 1) & mask) {
+            const uint32_t i = slots_[p];
+            if (i == kNone) break;
+            if (equal(i, s, n)) {
+                *inserted = false;
+                return i;
+            }
+        }
+        const uint32_t idx = size();
+        bytes_.insert(bytes_.end(), s, s + n);
+        off_.push_back((uint64_t)bytes_.size());
+        slots_[p] = idx;
+        if ((uint64_t)(idx + 1) * 10 > (uint64_t)slots_.size() * 6) grow();
+        *inserted = true;
+        return idx;
+    }
+    void clear() {
+        bytes_.clear();
+        off_.assign(1, 0);
+        slots_.assign(1024, kNone);
+    }
+
+  private:
+    static uint64_t hash(const char *s, size_t n) {
+        uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)n;
+        while (n >= 8) {
+            uint64_t w;
+            memcpy(&w, s, 8);
+            h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+            h ^= h >> 32;
+            s += 8;
+            n -= 8;
+        }
+        uint64_t w = 0;
+        memcpy(&w, s, n);
+        h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+        h ^= h >> 29;
+        return h * 0x9E3779B97F4A7C15ull >> 7;
+    }
+    bool equal(uint32_t i, const char *s, size_t n) const {
+        const uint64_t a = off_[i], b = off_[i + 1];
+        return (size_t)(b - a) == n && memcmp(bytes_.data() + a, s, n) == 0;
+    }
+    void grow() {
+        std::vector<uint32_t> ns(slots_.size() * 2, kNone);
+        const size_t mask = ns.size() - 1;
+        for (uint32_t i = 0; i < size(); ++i) {
+            size_t n;
+            const char *s = id(i, &n);
+            size_t p = (size_t)hash(s, n) & mask;
+            while (ns[p] != kNone) p = (p + 1) & mask;
+            ns[p] = i;
+        }
+        slots_.swap(ns);
+    }
+    std::vector<char> bytes_;
+    std::vector<uint64_t> off_{0};
+    std::vector<uint32_t> slots_;
+};
+
+struct PendingRecord {
+    uint32_t read, begin, end;
+};
+
+// Parse status of the text ingesters (ingest.cpp).
+struct IngestError {
+    int code = 0;         // yb_status
+    uint64_t line = 0;    // 1-based record number
+    std::string message;
+};
+
+class Engine;  // capi.cu
+
+// Parses a whole PAF (format 'p': tab-delimited, first 9 columns, src/io.rs:24-34) or BLASR m4
+// (format 'm': space-delimited, 12 columns, src/io.rs:37-50) buffer and feeds
+// add_overlap_and_length twice per record (src/reads2ovl/mod.rs:83-145). Returns false on error.
+typedef bool (*AddFn)(void *sink, const char *id, size_t id_len, uint32_t b, uint32_t e, uint64_t len);
+bool ingest_buffer(const char *text, size_t n, int format, AddFn add, void *sink, IngestError *err);
+
+}  // namespace yb
