@@ -169,11 +169,15 @@ def main():
     fm = yb.FullMemory(device=local_rank)
     fm.bind_csr(csr)
     fm.upload()
+    fm.synchronize()
     _, _, counts = ybd.shard_layout(n_glob, world)
     slot = ybd.bitmap_bytes(int(counts.max()))
     gathered = torch.zeros(world, slot, dtype=torch.uint8, device=dev)
     fm.bind_device_bitmap(gathered[rank].data_ptr(), slot)
-    stream = torch.cuda.current_stream()
+    # a non-default stream: the C ABI takes NULL as "the context's own stream", and CUDA events only see
+    # the stream they are recorded on, so kernels, all-gather and events all go to this one
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     flush = None
     in_bytes = csr.nbytes
     if in_bytes < 2 * L2_BYTES:  # shard smaller than ~2x L2: flush L2 between timed iterations
