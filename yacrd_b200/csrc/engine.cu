@@ -111,7 +111,7 @@ struct yb_ctx {
     PinnedBuf<uint2> h_iv;
     std::vector<uint32_t> arrival_rowptr;  // KEEP_HOST_INTERVALS
     uint32_t n_reads = 0, n_iv = 0, max_k = 0;
-    uint64_t huge_keys = 0;
+    yb::RowStats rows;
     bool frozen = false, uploaded = false, computed = false, downloaded = false, from_report = false;
 
     // ---- device ----
@@ -193,6 +193,15 @@ int intern_read(yb_ctx *c, const char *id, size_t n, bool *is_new, uint32_t *idx
     return YB_OK;
 }
 
+inline void add_row(yb::RowStats *rs, uint64_t k) {
+    const uint64_t bp = yb::big_pairs_for_row(k);
+    if (bp) {
+        rs->n_big += 1;
+        rs->big_pairs += bp;
+        rs->huge_keys += yb::huge_keys_for_row(k);
+    }
+}
+
 // Freeze: counting sort of the arrival-order records by read -> CSR in pinned memory. Within a read the
 // arrival order is kept (the kernels sort anyway; yb_overlap shows arrival order like Reads2Ovl::overlap).
 int freeze(yb_ctx *c) {
@@ -200,19 +209,19 @@ int freeze(yb_ctx *c) {
     if (c->b_rowptr) {  // borrowed CSR: only derive the row statistics
         const uint32_t n = c->n_indexed;
         uint32_t mk = 0;
-        uint64_t huge = 0;
+        yb::RowStats rs;
         for (uint32_t r = 0; r < n; ++r) {
             if (c->b_rowptr[r + 1] < c->b_rowptr[r]) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr is not monotone at read %u", r);
             if (c->b_len[r] > yb::kMaxLength) return c->fail(YB_ERR_TOO_LARGE, "read %u is longer than 2^31-1 bases", r);
             const uint32_t k = c->b_rowptr[r + 1] - c->b_rowptr[r];
             mk = std::max(mk, k);
-            huge += yb::huge_keys_for_row(k);
+            add_row(&rs, k);
         }
         c->n_reads = n;
         c->n_iv = n ? c->b_rowptr[n] - c->b_rowptr[0] : 0;
         if (n && c->b_rowptr[0] != 0) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr[0] must be 0");
         c->max_k = mk;
-        c->huge_keys = huge;
+        c->rows = rs;
         c->frozen = true;
         return YB_OK;
     }
@@ -225,10 +234,10 @@ int freeze(yb_ctx *c) {
     memset(rp, 0, sizeof(uint32_t) * ((size_t)n + 1));
     for (size_t i = 0; i < m; ++i) rp[c->pending[i].read + 1]++;
     uint32_t mk = 0;
-    uint64_t huge = 0;
+    yb::RowStats rs;
     for (uint32_t r = 0; r < n; ++r) {
         mk = std::max(mk, rp[r + 1]);
-        huge += yb::huge_keys_for_row(rp[r + 1]);
+        add_row(&rs, rp[r + 1]);
         rp[r + 1] += rp[r];
     }
     std::vector<uint32_t> cur(rp, rp + n);
@@ -244,7 +253,7 @@ int freeze(yb_ctx *c) {
     c->n_reads = n;
     c->n_iv = (uint32_t)m;
     c->max_k = mk;
-    c->huge_keys = huge;
+    c->rows = rs;
     c->frozen = true;
     return YB_OK;
 }
@@ -349,7 +358,7 @@ int yb_reset(yb_ctx *c) {
     c->n_indexed = 0;
     c->b_rowptr = c->b_iv = c->b_len = nullptr;
     c->n_reads = c->n_iv = c->max_k = c->n_gaps = 0;
-    c->huge_keys = 0;
+    c->rows = yb::RowStats();
     c->from_report = false;
     c->invalidate();
     return YB_OK;
@@ -449,13 +458,13 @@ int yb_add_csr(yb_ctx *c, const uint32_t *rowptr, const uint32_t *iv, const uint
             c->h_rowptr.p[0] = 0;
         }
         uint32_t mk = old_n ? c->max_k : 0;
-        uint64_t huge = old_n ? c->huge_keys : 0;
+        yb::RowStats rs = old_n ? c->rows : yb::RowStats();
         for (uint32_t r = 0; r < n_reads; ++r) {
             if (rowptr[r + 1] < rowptr[r]) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr is not monotone at read %u", r);
             if (length[r] > yb::kMaxLength) return c->fail(YB_ERR_TOO_LARGE, "read %u is longer than 2^31-1 bases", r);
             const uint32_t k = rowptr[r + 1] - rowptr[r];
             mk = std::max(mk, k);
-            huge += yb::huge_keys_for_row(k);
+            add_row(&rs, k);
             c->h_rowptr.p[old_n + r + 1] = (uint32_t)(old_m + (rowptr[r + 1] - rowptr[0]));
             c->h_len.p[old_n + r] = length[r];
         }
@@ -465,7 +474,7 @@ int yb_add_csr(yb_ctx *c, const uint32_t *rowptr, const uint32_t *iv, const uint
         c->n_reads = (uint32_t)tn;
         c->n_iv = (uint32_t)(old_m + add_m);
         c->max_k = mk;
-        c->huge_keys = huge;
+        c->rows = rs;
         c->invalidate();
         c->frozen = true;
         return YB_OK;
@@ -602,7 +611,7 @@ int yb_upload(yb_ctx *c) {
     if (!c->d_rowptr.reserve(n + 1) || !c->d_len.reserve(n + 1) || !c->d_iv.reserve(m + 2))
         return c->fail(YB_ERR_NOMEM, "device allocation failed (%zu reads, %zu intervals)", n, m);
     if (int rc = ensure_result_buffers(c)) return rc;
-    const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->max_k, c->huge_keys);
+    const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->rows);
     if (!c->d_scratch.reserve(sb)) return c->fail(YB_ERR_NOMEM, "device scratch allocation failed (%zu bytes)", sb);
     if (n) {
         YB_CUDA(c, cudaMemcpyAsync(c->d_rowptr.p, c->rowptr_host(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, c->stream));
@@ -634,6 +643,7 @@ int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *s
         a.n_reads = c->n_reads;
         a.n_iv = c->n_iv;
         a.max_k = c->max_k;
+        a.rows = c->rows;
         a.cls = c->d_cls.p;
         a.gap_ptr = c->d_gap_ptr.p;
         a.gaps = c->d_gaps.p;

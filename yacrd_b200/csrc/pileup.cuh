@@ -17,12 +17,20 @@ enum Counter : uint32_t {
     kCntNotCovered = 2,
     kCntMalformed = 3,   // intervals violating 0 <= begin < end <= length
     kCntTile = 4,        // dynamic tile scheduler
-    kCntBigList = 5,     // reads deferred to the CTA tier
-    kCntHugeBump = 6,    // bump allocator (in u32 keys) of the global-scratch tier, low word
+    kCntBigList = 5,     // rows with more than 256 intervals (big tier)
+    kCntHugeBump = 6,    // bump allocator (in u32 keys) of the global-scratch tier
+    kCntBigBump = 7,     // bump allocator (in pairs) of the big tier's side buffer
     kCntTierWarp = 8,    // reads taken by each tier
     kCntTierCta = 9,
     kCntTierHuge = 10,
     kNumCounters = 16
+};
+
+// What the host knows about the rows at freeze time (sizes the scratch exactly).
+struct RowStats {
+    uint64_t n_big = 0;      // rows with k > 256
+    uint64_t big_pairs = 0;  // sum over them of k + 1 (side buffer of their bad regions)
+    uint64_t huge_keys = 0;  // sum over rows beyond the shared-memory tier of next_pow2(2k)
 };
 
 struct DetectArgs {
@@ -33,6 +41,7 @@ struct DetectArgs {
     uint32_t n_reads;
     uint32_t n_iv;
     uint32_t max_k;          // largest row (host knows it from the row pointers)
+    RowStats rows;
     // outputs, resident in HBM
     uint8_t *cls;            // n_reads, yb_read_type
     uint32_t *gap_ptr;       // n_reads + 1: exclusive scan of per-read bad-region counts
@@ -45,10 +54,10 @@ struct DetectArgs {
 };
 
 // Bytes of scratch launch_detect needs for a CSR of this shape.
-size_t detect_scratch_bytes(uint32_t n_reads, uint32_t n_iv, uint32_t max_k, uint64_t huge_keys);
-// Keys (u32) of global scratch one read with k intervals needs when it exceeds the shared-memory tier
-// (0 otherwise). The engine sums this over the rows at freeze time.
+size_t detect_scratch_bytes(uint32_t n_reads, uint32_t n_iv, const RowStats &rs);
+// Per-row contributions to RowStats (the engine sums them over the rows at freeze time).
 uint64_t huge_keys_for_row(uint64_t k);
+uint64_t big_pairs_for_row(uint64_t k);
 
 // Enqueues one whole detect step on `stream`. Returns the number of kernel launches enqueued, or -1
 // on a launch error.
