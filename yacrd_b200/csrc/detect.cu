@@ -83,15 +83,17 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 constexpr int E = 16;                          // keys per lane per array in the register tier
 constexpr uint32_t kSmallMaxK = 256;           // register tier: rows with k <= 256 (G = 16 lanes x 16 keys)
 #ifndef YB_TILE_W
-#define YB_TILE_W 4096
+#define YB_TILE_W 1024
 #endif
 constexpr uint32_t kTileW = YB_TILE_W;         // tile = rows whose weight rowptr[r] + 8r falls in one window
 constexpr uint32_t kReadW = 8;
 constexpr uint32_t kMaxTileReads = kTileW / kReadW;
 constexpr uint32_t kSlabCap = kTileW + kSmallMaxK + 64;  // intervals staged per tile (+ alignment slack per run)
-constexpr uint32_t kFusedThreads = 128;
-constexpr uint32_t kFusedWarps = kFusedThreads / 32;
-constexpr uint32_t kScratchWords = 832;        // per warp: (32/G) groups x 17 (G+1) words, max at G = 2 (816)
+#ifndef YB_FUSED_WARPS
+#define YB_FUSED_WARPS 2
+#endif
+constexpr uint32_t kFusedWarps = YB_FUSED_WARPS;
+constexpr uint32_t kFusedThreads = kFusedWarps * 32;
 constexpr uint32_t kBigThreads = 512;
 constexpr uint32_t kBigSmemEvents = 16384;     // big_kernel: 64 KB of u32 event keys in shared memory
 
@@ -316,7 +318,8 @@ __global__ void __launch_bounds__(kBigThreads) big_kernel(DetectArgs a, Work w, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// register tier: G lanes per row, E = 16 keys per lane per array, blocked layout (element = g*16 + t)
+// register tier: G lanes per row (G = 2..16, per lane at run time), E = 16 keys per lane per array,
+// blocked layout (element = g*16 + t): shuffles only on the log2(G) outermost merge levels.
 // ------------------------------------------------------------------------------------------------
 // Batcher odd-even merge sort of the 16 keys a lane holds (63 compare-exchanges, no shuffles).
 __device__ __forceinline__ void sort16(uint32_t (&k)[E]) {
@@ -330,54 +333,62 @@ __device__ __forceinline__ void sort16(uint32_t (&k)[E]) {
 #undef CE
 }
 
-// Sorts the 16*G keys of each group of G lanes (ascending in element order g*16 + t). After sort16 every
-// lane holds a sorted run; each bitonic merge level of LS lanes costs 1 + log2(LS) - 1 shuffle steps on the
-// lane bits and 4 in-register half-cleaner steps on the slot bits.
-template <int G>
-__device__ __forceinline__ void sort_group(uint32_t (&key)[E]) {
+// Sorts, for every group of G lanes, its 16*G keys (ascending in element order g*16 + t). G is a per-lane
+// run-time value (groups of different sizes share a warp, larger groups on lower lanes); gmax is the
+// warp's largest G. One rolled loop serves every group size and both arrays, so the code stays small
+// enough for the instruction caches.
+__device__ __forceinline__ void sort_group(uint32_t (&key)[E], uint32_t G, uint32_t gmax) {
     sort16(key);
     const uint32_t lane = lane_id();
-#pragma unroll
-    for (int ls = 2; ls <= G; ls <<= 1) {
+#pragma unroll 1
+    for (uint32_t ls = 2; ls <= gmax; ls <<= 1) {
+        const bool on = ls <= G;
         {   // flip: element e pairs with e ^ (16*ls - 1): partner lane ^ (ls-1), slot 15 - t
-            const bool keep_min = (lane & (uint32_t)(ls >> 1)) == 0;
+            const bool keep_min = (lane & (ls >> 1)) == 0;
             uint32_t other[E];
 #pragma unroll
             for (int t = 0; t < E; ++t) other[t] = __shfl_xor_sync(FULL, key[E - 1 - t], ls - 1);
+            if (on) {
 #pragma unroll
-            for (int t = 0; t < E; ++t) key[t] = keep_min ? min(key[t], other[t]) : max(key[t], other[t]);
+                for (int t = 0; t < E; ++t) key[t] = keep_min ? min(key[t], other[t]) : max(key[t], other[t]);
+            }
         }
-#pragma unroll
-        for (int j = ls >> 2; j > 0; j >>= 1) {  // half-cleaners on the lane bits
-            const bool keep_min = (lane & (uint32_t)j) == 0;
+#pragma unroll 1
+        for (uint32_t j = ls >> 2; j > 0; j >>= 1) {  // half-cleaners on the lane bits
+            const bool keep_min = (lane & j) == 0;
 #pragma unroll
             for (int t = 0; t < E; ++t) {
                 const uint32_t o = __shfl_xor_sync(FULL, key[t], j);
-                key[t] = keep_min ? min(key[t], o) : max(key[t], o);
+                if (on) key[t] = keep_min ? min(key[t], o) : max(key[t], o);
             }
         }
+        if (on) {
 #pragma unroll
-        for (int s = E >> 1; s > 0; s >>= 1) {  // half-cleaners on the slot bits
+            for (int s = E >> 1; s > 0; s >>= 1) {  // half-cleaners on the slot bits
 #pragma unroll
-            for (int t = 0; t < E; ++t)
-                if ((t & s) == 0) ce(key[t], key[t | s]);
+                for (int t = 0; t < E; ++t)
+                    if ((t & s) == 0) ce(key[t], key[t | s]);
+            }
         }
     }
 }
 
-struct TileSmem {
-    // per-tile row metadata (row i of the tile = read r0 + i)
-    uint32_t row[kMaxTileReads + 1];   // rowptr values
+constexpr uint32_t kScratchWords = 17u * 33u + 3u;  // 33 blocks of 16 keys at a 17-word pitch
+
+struct alignas(16) WarpSmem {  // one per warp: a warp runs its tiles on its own, no CTA-wide barrier anywhere
+    unsigned long long mbar;
+    uint32_t row[kMaxTileReads + 1];   // rowptr values of the tile's rows (row i = read r0 + i)
     uint32_t len[kMaxTileReads];
     uint32_t meta[kMaxTileReads];      // n_gaps | h << 30 | tail << 31; big rows: n_gaps
     uint32_t goff[kMaxTileReads];      // exclusive scan of n_gaps inside the tile
     uint16_t soff[kMaxTileReads];      // slab offset (in intervals) of the row's data
-    uint16_t order[kMaxTileReads];     // rows grouped by size class
+    uint8_t order[kMaxTileReads];      // rows grouped by size class, largest first
     uint8_t cls[kMaxTileReads];
-    uint32_t class_cnt[4], class_base[4], batch_base[5];
-    uint32_t next_batch, tile, gap_base, n_big_in_tile, warp_tot[kFusedWarps], hist[3];
-    unsigned long long mbar;
+    uint32_t scr[kScratchWords];
 };
+static_assert(sizeof(WarpSmem) % 16 == 0, "slab must stay 16-byte aligned");
+constexpr size_t kWarpSmemBytes = sizeof(WarpSmem) + sizeof(uint2) * kSlabCap;
+static_assert(kMaxTileReads <= 128 && kMaxTileReads % 32 == 0, "row ids are u8; rows are walked 32 at a time");
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -408,17 +419,16 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  : "memory");
 }
 
-// One batch: 32/G rows of size class G, one row per group of G lanes.
-template <int G>
-__device__ __forceinline__ void process_batch(TileSmem &ts, uint2 *slab, uint32_t *scr, uint32_t first, uint32_t count,
-                                              uint32_t c, double not_cov, uint32_t *counters) {
-    constexpr uint32_t kGroupWords = 17u * (G + 1);
-    const uint32_t lane = lane_id(), grp = lane / G, g = lane % G;
-    const bool active = grp < count;
-    const uint32_t i_row = active ? ts.order[first + grp] : 0u;
-    const uint32_t k = active ? ts.row[i_row + 1] - ts.row[i_row] : 0u;
-    const uint32_t len = active ? ts.len[i_row] : 0u;
-    const uint2 *row = slab + ts.soff[i_row];
+// One batch of rows: lane p of the batch belongs to the group of G lanes that owns row i_row (valid lanes
+// only). Sorts the row's begins and ends, finds the crossings, leaves them in the row's slab slot and the
+// row's bad-region count / flags / class in ws.meta / ws.cls.
+__device__ __forceinline__ void process_batch(WarpSmem &ws, uint2 *slab, bool valid, uint32_t i_row, uint32_t G, uint32_t g,
+                                              uint32_t gmax, uint32_t c, double not_cov, uint32_t &malformed) {
+    const uint32_t lane = lane_id();
+    const uint32_t k = valid ? ws.row[i_row + 1] - ws.row[i_row] : 0u;
+    const uint32_t len = valid ? ws.len[i_row] : 0u;
+    const uint32_t so = valid ? ws.soff[i_row] : 0u;
+    const uint2 *row = slab + so;
     // striped load (conflict-free); the initial arrangement is irrelevant to the sort
     uint32_t B[E], En[E];
     bool bad_iv = false;
@@ -433,40 +443,44 @@ __device__ __forceinline__ void process_batch(TileSmem &ts, uint2 *slab, uint32_
         B[t] = v.x;
         En[t] = v.y;
     }
-    if (bad_iv) atomicAdd(counters + kCntMalformed, 1u);
-    sort_group<G>(B);
-    sort_group<G>(En);
-    // skewed copy of E (17-word pitch per 16-key block, one zero block in front): conflict-free for the
-    // blocked writers and for the shifted readers
-    uint32_t *q = scr + grp * kGroupWords;
-    __syncwarp();
-    if (g == 0) {
+    malformed += bad_iv;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the network sorts begins, then ends
+        sort_group(B, G, gmax);
 #pragma unroll
-        for (int t = 0; t < E; ++t) q[t] = 0u;
+        for (int t = 0; t < E; ++t) {
+            const uint32_t x = B[t];
+            B[t] = En[t];
+            En[t] = x;
+        }
     }
-#pragma unroll
-    for (int t = 0; t < E; ++t) q[17u * (g + 1) + t] = En[t];
+    // skewed copy of E (17-word pitch per 16-key block, lane l's block at 17 (l + 1)): conflict-free for
+    // the blocked writers and for the shifted readers
+    uint32_t *q = ws.scr + 17u * (lane + 1u);
     __syncwarp();
-    // Ev[t] = E[16 g + t - c - 1], t = 0..16
+#pragma unroll
+    for (int t = 0; t < E; ++t) q[t] = En[t];
+    __syncwarp();
+    // Ev[t] = E[16 g + t - c - 1], t = 0..16 (0 below the row's first end)
     uint32_t Ev[E + 1];
     if (c < 16u) {
-        // window of 18 consecutive words starting one block back; the pitch hole sits at index c + 1
-        const uint32_t *wptr = q + 17u * g + (15u - c);
+        // 18 consecutive words starting in the previous lane's block; the pitch hole sits at index c + 1
+        const uint32_t *wptr = q - 2u - c;
         uint32_t W[E + 2];
 #pragma unroll
         for (int t = 0; t < E + 2; ++t) W[t] = wptr[t];
 #pragma unroll
-        for (int t = 0; t < E + 1; ++t) Ev[t] = (uint32_t)t <= c ? W[t] : W[t + 1];
+        for (int t = 0; t < E + 1; ++t) Ev[t] = (uint32_t)t <= c ? (g == 0u ? 0u : W[t]) : W[t + 1];
     } else {
+        const uint32_t *q0 = q - 17u * g;  // the group's first block
 #pragma unroll
         for (int t = 0; t < E + 1; ++t) {
-            int e = (int)(16u * g + t) - (int)min(c, 0x7FFFFFF0u) - 1;
-            e = max(e, -1);
-            Ev[t] = q[17 + e + (e >> 4)];
+            const int e = (int)(16u * g + t) - (int)min(c, 0x7FFFFFF0u) - 1;
+            Ev[t] = e < 0 ? 0u : q0[e + (e >> 4)];
         }
     }
-    uint32_t Bnext = __shfl_down_sync(FULL, B[0], 1, G);
-    if (g == G - 1) Bnext = INF;
+    uint32_t Bnext = __shfl_down_sync(FULL, B[0], 1);
+    if (g == G - 1u) Bnext = INF;
     // X_t = B_t < Ev[t+1], Y_t = Ev[t] <= B_t; U = X_t & Y_t, D = X_t & Y_{t+1}
     uint32_t um = 0, dm = 0;
 #pragma unroll
@@ -477,19 +491,19 @@ __device__ __forceinline__ void process_batch(TileSmem &ts, uint2 *slab, uint32_
         if (x && y) um |= 1u << t;
         if (x && y1) dm |= 1u << t;
     }
-    // ranks of this lane's crossings among the row's ups / downs (packed scan over the group)
+    // ranks of this lane's crossings among the row's ups / downs (packed segmented scan over the group)
     const uint32_t mine = __popc(um) | (__popc(dm) << 16);
     uint32_t incl = mine;
-#pragma unroll
-    for (int off = 1; off < G; off <<= 1) {
-        const uint32_t o = __shfl_up_sync(FULL, incl, off, G);
-        if (g >= (uint32_t)off) incl += o;
+#pragma unroll 1
+    for (uint32_t off = 1; off < gmax; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(FULL, incl, off);
+        if (g >= off) incl += o;
     }
-    const uint32_t tot = __shfl_sync(FULL, incl, G - 1, G);
+    const uint32_t tot = __shfl_sync(FULL, incl, lane | (G - 1u));
     uint32_t ru = (incl - mine) & 0xFFFFu, rd = (incl - mine) >> 16;
     const uint32_t n_up = tot & 0xFFFFu;
     // crossings go back into the row's own slab slot (2k words, no longer needed): C[2j] = U_j, C[2j+1] = D_j
-    uint32_t *C = reinterpret_cast<uint32_t *>(slab + ts.soff[i_row]);
+    uint32_t *C = reinterpret_cast<uint32_t *>(slab + so);
     uint32_t acc = 0;
 #pragma unroll
     for (int t = 0; t < E; ++t) {
@@ -504,10 +518,13 @@ __device__ __forceinline__ void process_batch(TileSmem &ts, uint2 *slab, uint32_
             ++rd;
         }
     }
-#pragma unroll
-    for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+#pragma unroll 1
+    for (uint32_t off = gmax >> 1; off > 0; off >>= 1) {
+        const uint32_t o = __shfl_xor_sync(FULL, acc, off);
+        if (off < G) acc += o;
+    }
     __syncwarp();
-    if (active && g == 0) {
+    if (valid && g == 0u) {
         uint32_t ng, h, tail;
         if (n_up) {
             h = C[0] != 0u;
@@ -516,241 +533,198 @@ __device__ __forceinline__ void process_batch(TileSmem &ts, uint2 *slab, uint32_
         } else {
             ng = h = tail = len != 0u;
         }
-        ts.meta[i_row] = ng | (h << 30) | (tail << 31);
-        ts.cls[i_row] = (uint8_t)classify(len + acc, len, n_up, not_cov);
+        ws.meta[i_row] = ng | (h << 30) | (tail << 31);
+        ws.cls[i_row] = (uint8_t)classify(len + acc, len, n_up, not_cov);
     }
 }
 
 __global__ void __launch_bounds__(kFusedThreads) fused_kernel(DetectArgs a, Work w, uint32_t c, double not_cov) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint2 *slab = reinterpret_cast<uint2 *>(smem_raw);
-    uint32_t *scratch = reinterpret_cast<uint32_t *>(smem_raw + sizeof(uint2) * kSlabCap);
-    TileSmem &ts = *reinterpret_cast<TileSmem *>(smem_raw + sizeof(uint2) * kSlabCap + sizeof(uint32_t) * kScratchWords * kFusedWarps);
-    const uint32_t tid = threadIdx.x, lane = lane_id(), wid = tid >> 5;
-    uint32_t *scr = scratch + wid * kScratchWords;
-    if (tid == 0) {
-        mbar_init(&ts.mbar, 1);
+    const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
+    WarpSmem &ws = *reinterpret_cast<WarpSmem *>(smem_raw + wid * kWarpSmemBytes);
+    uint2 *slab = reinterpret_cast<uint2 *>(smem_raw + wid * kWarpSmemBytes + sizeof(WarpSmem));
+    if (lane == 0) {
+        mbar_init(&ws.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 3) ts.hist[tid] = 0;
-    uint32_t parity = 0;
-    __syncthreads();
-    for (;;) {
-        if (tid == 0) {
-            ts.tile = atomicAdd(a.counters + kCntTile, 1u);
-            ts.next_batch = 0;
-            ts.n_big_in_tile = 0;
-        }
-        if (tid < 4) ts.class_cnt[tid] = 0;
-        __syncthreads();
-        const uint32_t tile = ts.tile;
-        if (tile >= w.n_tiles) break;
+    __syncwarp();
+    uint32_t parity = 0, malformed = 0, hist0 = 0, hist1 = 0, hist2 = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    volatile unsigned long long *st = w.tile_status;
+    const uint32_t n_warps = gridDim.x * kFusedWarps;
+    // Static round-robin over tiles: every tile below the one a warp works on belongs to a resident warp
+    // that is at or before it in its own sequence, so the look-back below cannot deadlock.
+    for (uint32_t tile = blockIdx.x * kFusedWarps + wid; tile < w.n_tiles; tile += n_warps) {
         const uint32_t r0 = __ldg(w.tile_first + tile), r1 = __ldg(w.tile_first + tile + 1), R = r1 - r0;
         if (R == 0) {  // empty window: still a link of the look-back chain
-            if (tid == 0) {
+            if (lane == 0) {
                 unsigned long long v = 0;
                 if (tile) {
-                    do v = *reinterpret_cast<volatile unsigned long long *>(w.tile_status + tile - 1);
+                    do v = st[tile - 1];
                     while ((v >> 62) != 2ull);
                 }
-                *reinterpret_cast<volatile unsigned long long *>(w.tile_status + tile) = (2ull << 62) | (v & 0xFFFFFFFFull);
+                st[tile] = (2ull << 62) | (v & 0xFFFFFFFFull);
             }
-            __syncthreads();
             continue;
         }
-        for (uint32_t i = tid; i <= R; i += kFusedThreads) ts.row[i] = __ldg(a.rowptr + r0 + i);
-        for (uint32_t i = tid; i < R; i += kFusedThreads) ts.len[i] = __ldg(a.len + r0 + i);
-        __syncthreads();
-        // ---- rows -> size classes; trivial rows (k <= c: depth never exceeds c) are finished here ----
-        uint32_t my_pos[kMaxTileReads / kFusedThreads], my_cls[kMaxTileReads / kFusedThreads];
+#pragma unroll 1
+        for (uint32_t i = lane; i <= R; i += 32u) ws.row[i] = __ldg(a.rowptr + r0 + i);
+#pragma unroll 1
+        for (uint32_t i = lane; i < R; i += 32u) ws.len[i] = __ldg(a.len + r0 + i);
+        __syncwarp();
+        // ---- rows -> size classes (G = 2, 4, 8, 16 lanes); trivial rows (k <= c: depth never exceeds c)
+        //      are finished here; big rows (k > 256) were finished by big_kernel ----
+        uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+        uint32_t my_cls[kMaxTileReads / 32], my_rank[kMaxTileReads / 32];
         bool any_big = false;
 #pragma unroll
-        for (uint32_t u = 0; u < kMaxTileReads / kFusedThreads; ++u) {
-            const uint32_t i = tid + u * kFusedThreads;
-            my_cls[u] = 0xFFu;
+        for (uint32_t u = 0; u < kMaxTileReads / 32; ++u) {
+            const uint32_t i = u * 32u + lane;
+            uint32_t cl = 0xFFu;
             if (i < R) {
-                const uint32_t k = ts.row[i + 1] - ts.row[i], len = ts.len[i];
+                const uint32_t k = ws.row[i + 1] - ws.row[i], len = ws.len[i];
                 if (k > kSmallMaxK) {
-                    any_big = true;
-                    my_cls[u] = 0xFEu;
+                    cl = 0xFEu;
                 } else if (k <= c) {
                     const uint32_t ng = len != 0u;
-                    ts.meta[i] = ng | (ng << 30) | (ng << 31);
-                    ts.cls[i] = (uint8_t)classify(len, len, 0u, not_cov);
+                    ws.meta[i] = ng | (ng << 30) | (ng << 31);
+                    ws.cls[i] = (uint8_t)classify(len, len, 0u, not_cov);
                     if (k) {  // still validate the intervals of a row that is not sorted
-                        const uint2 *gi = a.iv + ts.row[i];
+                        const uint2 *gi = a.iv + ws.row[i];
                         bool bad = false;
+#pragma unroll 1
                         for (uint32_t j = 0; j < k; ++j) {
                             const uint2 v = __ldg(gi + j);
                             bad |= !(v.x < v.y && v.y <= len);
                         }
-                        if (bad) atomicAdd(a.counters + kCntMalformed, 1u);
+                        malformed += bad;
                     }
                 } else {
-                    const uint32_t cl = k <= 32u ? 0u : (k <= 64u ? 1u : (k <= 128u ? 2u : 3u));
-                    my_cls[u] = cl;
-                    my_pos[u] = atomicAdd(&ts.class_cnt[cl], 1u);
+                    cl = k <= 32u ? 0u : (k <= 64u ? 1u : (k <= 128u ? 2u : 3u));
                 }
             }
+            any_big |= cl == 0xFEu;
+            const uint32_t m0 = __ballot_sync(FULL, cl == 0u), m1 = __ballot_sync(FULL, cl == 1u);
+            const uint32_t m2 = __ballot_sync(FULL, cl == 2u), m3 = __ballot_sync(FULL, cl == 3u);
+            my_cls[u] = cl;
+            my_rank[u] = cl == 0u ? cnt0 + __popc(m0 & lt)
+                       : cl == 1u ? cnt1 + __popc(m1 & lt)
+                       : cl == 2u ? cnt2 + __popc(m2 & lt) : cnt3 + __popc(m3 & lt);
+            cnt0 += __popc(m0);
+            cnt1 += __popc(m1);
+            cnt2 += __popc(m2);
+            cnt3 += __popc(m3);
         }
-        const int tile_has_big = __syncthreads_or(any_big);
-        if (tid == 0) {
-            // batches: largest rows first (longest jobs first)
-            uint32_t b = 0, o = 0;
-            for (int cl = 3; cl >= 0; --cl) {
-                const uint32_t per = 16u >> cl;  // rows per batch: 16, 8, 4, 2
-                ts.batch_base[3 - cl] = b;
-                ts.class_base[cl] = o;
-                b += (ts.class_cnt[cl] + per - 1u) / per;
-                o += ts.class_cnt[cl];
-            }
-            ts.batch_base[4] = b;
-            // ---- stage the tile's interval slab: TMA bulk copies, one per run of non-big rows ----
+        const bool tile_has_big = __any_sync(FULL, any_big);
+        // row order: class 3 (G = 16) first; lane position p of a row = lane base of its class + rank * G
+        const uint32_t rb3 = 0, rb2 = cnt3, rb1 = rb2 + cnt2, rb0 = rb1 + cnt1;
+        const uint32_t lb3 = 0, lb2 = 16u * cnt3, lb1 = lb2 + 8u * cnt2, lb0 = lb1 + 4u * cnt1, lanes_total = lb0 + 2u * cnt0;
+#pragma unroll
+        for (uint32_t u = 0; u < kMaxTileReads / 32; ++u) {
+            const uint32_t i = u * 32u + lane, cl = my_cls[u];
+            if (cl < 4u) ws.order[(cl == 0u ? rb0 : cl == 1u ? rb1 : cl == 2u ? rb2 : rb3) + my_rank[u]] = (uint8_t)i;
+            if (i < R && !tile_has_big) ws.soff[i] = (uint16_t)(ws.row[i] - (ws.row[0] & ~1u));
+        }
+        // ---- stage the tile's interval slab: TMA bulk copies, one per run of non-big rows ----
+        if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            uint32_t bytes_total = 0;
             if (!tile_has_big) {
-                const uint32_t gs = ts.row[0], ge = ts.row[R];
-                const uint32_t cs = gs & ~1u, ce_ = (ge + 1u) & ~1u;
-                bytes_total = (ce_ - cs) * 8u;
-                mbar_expect_tx(&ts.mbar, bytes_total);
-                if (bytes_total) tma_load_1d(slab, a.iv + cs, bytes_total, &ts.mbar);
+                const uint32_t cs = ws.row[0] & ~1u, ce_ = (ws.row[R] + 1u) & ~1u, nb = (ce_ - cs) * 8u;
+                mbar_expect_tx(&ws.mbar, nb);
+                if (nb) tma_load_1d(slab, a.iv + cs, nb, &ws.mbar);
             } else {
-                // first pass: total bytes; second pass: issue (expect_tx must precede completion)
-                for (int pass = 0; pass < 2; ++pass) {
+                uint32_t bytes_total = 0;
+                for (int pass = 0; pass < 2; ++pass) {  // expect_tx must precede the copies
                     uint32_t d = 0, i = 0;
                     while (i < R) {
-                        while (i < R && ts.row[i + 1] - ts.row[i] > kSmallMaxK) ++i;
+                        while (i < R && ws.row[i + 1] - ws.row[i] > kSmallMaxK) {
+                            ws.soff[i] = 0;
+                            ++i;
+                        }
                         if (i >= R) break;
                         uint32_t j = i;
-                        while (j < R && ts.row[j + 1] - ts.row[j] <= kSmallMaxK) ++j;
-                        const uint32_t gs = ts.row[i], ge = ts.row[j];
-                        const uint32_t cs = gs & ~1u, ce_ = (ge + 1u) & ~1u, nb = (ce_ - cs) * 8u;
+                        const uint32_t cs = ws.row[i] & ~1u;
+                        while (j < R && ws.row[j + 1] - ws.row[j] <= kSmallMaxK) {
+                            ws.soff[j] = (uint16_t)(d + (ws.row[j] - cs));
+                            ++j;
+                        }
+                        const uint32_t ce_ = (ws.row[j] + 1u) & ~1u, nb = (ce_ - cs) * 8u;
                         if (pass == 0) bytes_total += nb;
-                        else if (nb) tma_load_1d(slab + d, a.iv + cs, nb, &ts.mbar);
+                        else if (nb) tma_load_1d(slab + d, a.iv + cs, nb, &ws.mbar);
                         d += ce_ - cs;
                         i = j;
                     }
-                    if (pass == 0) mbar_expect_tx(&ts.mbar, bytes_total);
+                    if (pass == 0) mbar_expect_tx(&ws.mbar, bytes_total);
                 }
             }
         }
-        __syncthreads();
-        // scatter rows into class order; slab offsets
-#pragma unroll
-        for (uint32_t u = 0; u < kMaxTileReads / kFusedThreads; ++u) {
-            const uint32_t i = tid + u * kFusedThreads;
-            if (i < R && my_cls[u] < 4u) ts.order[ts.class_base[my_cls[u]] + my_pos[u]] = (uint16_t)i;
-            if (i < R && !tile_has_big) ts.soff[i] = (uint16_t)(ts.row[i] - (ts.row[0] & ~1u));
-        }
-        if (tile_has_big && tid == 0) {
-            uint32_t d = 0, i = 0;
-            while (i < R) {
-                while (i < R && ts.row[i + 1] - ts.row[i] > kSmallMaxK) {
-                    ts.soff[i] = 0;
-                    ++i;
-                }
-                if (i >= R) break;
-                uint32_t j = i;
-                const uint32_t gs = ts.row[i], cs = gs & ~1u;
-                while (j < R && ts.row[j + 1] - ts.row[j] <= kSmallMaxK) {
-                    ts.soff[j] = (uint16_t)(d + (ts.row[j] - cs));
-                    ++j;
-                }
-                d += ((ts.row[j] + 1u) & ~1u) - cs;
-                i = j;
-            }
-        }
-        __syncthreads();
-        mbar_wait(&ts.mbar, parity);
+        __syncwarp();
+        mbar_wait(&ws.mbar, parity);
         parity ^= 1u;
-        // ---- pass A: sort + crossings, one batch per warp at a time ----
-        const uint32_t n_batches = ts.batch_base[4];
-        for (;;) {
-            uint32_t b = 0;
-            if (lane == 0) b = atomicAdd(&ts.next_batch, 1u);
-            b = __shfl_sync(FULL, b, 0);
-            if (b >= n_batches) break;
-            if (b < ts.batch_base[1]) {
-                const uint32_t j = b - ts.batch_base[0], first = ts.class_base[3] + j * 2u;
-                process_batch<16>(ts, slab, scr, first, min(2u, ts.class_cnt[3] - j * 2u), c, not_cov, a.counters);
-            } else if (b < ts.batch_base[2]) {
-                const uint32_t j = b - ts.batch_base[1], first = ts.class_base[2] + j * 4u;
-                process_batch<8>(ts, slab, scr, first, min(4u, ts.class_cnt[2] - j * 4u), c, not_cov, a.counters);
-            } else if (b < ts.batch_base[3]) {
-                const uint32_t j = b - ts.batch_base[2], first = ts.class_base[1] + j * 8u;
-                process_batch<4>(ts, slab, scr, first, min(8u, ts.class_cnt[1] - j * 8u), c, not_cov, a.counters);
-            } else {
-                const uint32_t j = b - ts.batch_base[3], first = ts.class_base[0] + j * 16u;
-                process_batch<2>(ts, slab, scr, first, min(16u, ts.class_cnt[0] - j * 16u), c, not_cov, a.counters);
-            }
+        // ---- pass A: sort + crossings, 32 lanes of rows at a time ----
+        for (uint32_t p0 = 0; p0 < lanes_total; p0 += 32u) {
+            const uint32_t p = p0 + lane;
+            const bool valid = p < lanes_total;
+            const uint32_t cl = p < lb2 ? 3u : (p < lb1 ? 2u : (p < lb0 ? 1u : 0u));
+            const uint32_t G = 2u << cl;
+            const uint32_t rel = p - (cl == 3u ? lb3 : cl == 2u ? lb2 : cl == 1u ? lb1 : lb0);
+            const uint32_t rank = rel >> (cl + 1u), g = rel & (G - 1u);
+            const uint32_t i_row = valid ? ws.order[(cl == 0u ? rb0 : cl == 1u ? rb1 : cl == 2u ? rb2 : rb3) + rank] : 0u;
+            const uint32_t gmax = __shfl_sync(FULL, G, 0);  // classes are laid out largest first
+            process_batch(ws, slab, valid, i_row, G, g, gmax, c, not_cov, malformed);
         }
-        if (tile_has_big) {  // big rows were finished by big_kernel: fetch their counts and classes
-            for (uint32_t i = tid; i < R; i += kFusedThreads)
-                if (ts.row[i + 1] - ts.row[i] > kSmallMaxK) {
+        if (tile_has_big) {
+            for (uint32_t i = lane; i < R; i += 32u)
+                if (ws.row[i + 1] - ws.row[i] > kSmallMaxK) {
                     const uint32_t j = w.big_slot[r0 + i];
-                    ts.meta[i] = w.big_cnt[j];
-                    ts.cls[i] = w.big_cls[j];
+                    ws.meta[i] = w.big_cnt[j];
+                    ws.cls[i] = w.big_cls[j];
                 }
         }
-        __syncthreads();
+        __syncwarp();
         // ---- exclusive scan of the bad-region counts over the tile's rows (row order) ----
-        {
-            constexpr uint32_t kPer = kMaxTileReads / kFusedThreads;
-            uint32_t v[kPer], s = 0;
+        constexpr uint32_t kPer = kMaxTileReads / 32;
+        uint32_t v[kPer], s = 0;
 #pragma unroll
-            for (uint32_t u = 0; u < kPer; ++u) {
-                const uint32_t i = tid * kPer + u;
-                v[u] = i < R ? (ts.meta[i] & 0x3FFFFFFFu) : 0u;
-                s += v[u];
-            }
-            const uint32_t incl = warp_incl_scan(s);
-            if (lane == 31) ts.warp_tot[wid] = incl;
-            __syncthreads();
-            uint32_t pre = incl - s, tile_total = 0;
-#pragma unroll
-            for (uint32_t q2 = 0; q2 < kFusedWarps; ++q2) {
-                if (q2 < wid) pre += ts.warp_tot[q2];
-                tile_total += ts.warp_tot[q2];
-            }
-#pragma unroll
-            for (uint32_t u = 0; u < kPer; ++u) {
-                const uint32_t i = tid * kPer + u;
-                if (i < R) ts.goff[i] = pre;
-                pre += v[u];
-            }
-            // ---- decoupled look-back over the tiles before this one (warp 0) ----
-            if (wid == 0) {
-                volatile unsigned long long *st = w.tile_status;
-                if (lane == 0) st[tile] = ((tile ? 1ull : 2ull) << 62) | tile_total;
-                uint32_t excl = 0;
-                if (tile) {
-                    int look = (int)tile - 1;
-                    for (;;) {
-                        const int idx = look - (int)lane;
-                        unsigned long long sv = (2ull << 62);
-                        if (idx >= 0) sv = st[idx];
-                        const uint32_t flag = (uint32_t)(sv >> 62);
-                        const uint32_t inval = __ballot_sync(FULL, flag == 0u);
-                        const uint32_t incl_m = __ballot_sync(FULL, flag == 2u);
-                        const uint32_t upto = incl_m ? ((2u << (__ffs(incl_m) - 1)) - 1u) : FULL;
-                        if (inval & upto) continue;  // a needed predecessor has not published yet
-                        uint32_t val = ((1u << lane) & upto) ? (uint32_t)sv : 0u;
-                        excl += warp_sum(val);
-                        if (incl_m) break;
-                        look -= 32;
-                    }
-                    if (lane == 0) st[tile] = (2ull << 62) | (unsigned long long)(excl + tile_total);
-                }
-                if (lane == 0) ts.gap_base = excl;
-            }
+        for (uint32_t u = 0; u < kPer; ++u) {
+            const uint32_t i = lane * kPer + u;
+            v[u] = i < R ? (ws.meta[i] & 0x3FFFFFFFu) : 0u;
+            s += v[u];
         }
-        __syncthreads();
+        const uint32_t incl = warp_incl_scan(s);
+        const uint32_t tile_total = __shfl_sync(FULL, incl, 31);
+        uint32_t pre = incl - s;
+#pragma unroll
+        for (uint32_t u = 0; u < kPer; ++u) {
+            const uint32_t i = lane * kPer + u;
+            if (i < R) ws.goff[i] = pre;
+            pre += v[u];
+        }
+        // ---- decoupled look-back over the tiles before this one ----
+        if (lane == 0) st[tile] = ((tile ? 1ull : 2ull) << 62) | tile_total;
+        uint32_t excl = 0;
+        if (tile) {
+            int look = (int)tile - 1;
+            for (;;) {
+                const int idx = look - (int)lane;
+                unsigned long long sv = (2ull << 62);
+                if (idx >= 0) sv = st[idx];
+                const uint32_t flag = (uint32_t)(sv >> 62);
+                const uint32_t inval = __ballot_sync(FULL, flag == 0u);
+                const uint32_t incl_m = __ballot_sync(FULL, flag == 2u);
+                const uint32_t upto = incl_m ? ((2u << (__ffs(incl_m) - 1)) - 1u) : FULL;
+                if (inval & upto) continue;  // a needed predecessor has not published yet
+                excl += warp_sum(((1u << lane) & upto) ? (uint32_t)sv : 0u);
+                if (incl_m) break;
+                look -= 32;
+            }
+            if (lane == 0) st[tile] = (2ull << 62) | (unsigned long long)(excl + tile_total);
+        }
+        __syncwarp();
         // ---- pass B: results to HBM, once, in final position ----
-        const uint32_t gap_base = ts.gap_base;
-        uint32_t hist0 = 0, hist1 = 0, hist2 = 0;
-        for (uint32_t i = tid; i < R; i += kFusedThreads) {
-            const uint32_t m = ts.meta[i], len = ts.len[i], k = ts.row[i + 1] - ts.row[i];
-            const uint32_t base = gap_base + ts.goff[i], cl = ts.cls[i];
+        for (uint32_t i = lane; i < R; i += 32u) {
+            const uint32_t m = ws.meta[i], len = ws.len[i], k = ws.row[i + 1] - ws.row[i];
+            const uint32_t base = excl + ws.goff[i], cl = ws.cls[i];
             a.gap_ptr[r0 + i] = base;
             a.cls[r0 + i] = (uint8_t)cl;
             hist0 += cl == 0u;
@@ -762,7 +736,7 @@ __global__ void __launch_bounds__(kFusedThreads) fused_kernel(DetectArgs a, Work
                 for (uint32_t gq = 0; gq < m; ++gq) a.gaps[base + gq] = src[gq];
             } else {
                 const uint32_t ng = m & 0x3FFFFFFFu, h = (m >> 30) & 1u, tail = m >> 31;
-                const uint32_t *C = reinterpret_cast<const uint32_t *>(slab + ts.soff[i]);
+                const uint32_t *C = reinterpret_cast<const uint32_t *>(slab + ws.soff[i]);
                 for (uint32_t gq = 0; gq < ng; ++gq) {
                     const uint32_t f0 = 2u * gq, f1 = f0 + 1u;
                     uint2 o;
@@ -772,36 +746,35 @@ __global__ void __launch_bounds__(kFusedThreads) fused_kernel(DetectArgs a, Work
                 }
             }
         }
-        hist0 = warp_sum(hist0);
-        hist1 = warp_sum(hist1);
-        hist2 = warp_sum(hist2);
-        if (lane == 0) {
-            if (hist0) atomicAdd(&ts.hist[0], hist0);
-            if (hist1) atomicAdd(&ts.hist[1], hist1);
-            if (hist2) atomicAdd(&ts.hist[2], hist2);
-        }
         // 2-bit bitmap: word j covers reads 16 j .. 16 j + 15; words shared with a neighbour tile are OR-ed
         {
             const uint32_t w0 = r0 >> 4, w1 = (r1 - 1u) >> 4;
-            for (uint32_t wj = w0 + tid; wj <= w1; wj += kFusedThreads) {
+            for (uint32_t wj = w0 + lane; wj <= w1; wj += 32u) {
                 const uint32_t lo = max(wj << 4, r0), hi = min((wj << 4) + 16u, r1);
                 uint32_t bits = 0;
-                for (uint32_t r = lo; r < hi; ++r) bits |= (uint32_t)ts.cls[r - r0] << (2u * (r & 15u));
+#pragma unroll 1
+                for (uint32_t r = lo; r < hi; ++r) bits |= (uint32_t)ws.cls[r - r0] << (2u * (r & 15u));
                 uint32_t *dst = reinterpret_cast<uint32_t *>(a.bitmap) + wj;
                 if (hi - lo == 16u) *dst = bits;
                 else if (bits) atomicOr(dst, bits);
             }
         }
-        __syncthreads();
-        if (tid < 3 && ts.hist[tid]) {
-            atomicAdd(a.counters + kCntNotBad + tid, ts.hist[tid]);
-            ts.hist[tid] = 0;
-        }
-        if (r1 == a.n_reads && tid == 0) a.gap_ptr[a.n_reads] = gap_base + ts.goff[R - 1] + (ts.meta[R - 1] & 0x3FFFFFFFu);
+        if (r1 == a.n_reads && lane == 0) a.gap_ptr[a.n_reads] = excl + tile_total;
+        __syncwarp();
+    }
+    hist0 = warp_sum(hist0);
+    hist1 = warp_sum(hist1);
+    hist2 = warp_sum(hist2);
+    malformed = warp_sum(malformed);
+    if (lane == 0) {
+        if (hist0) atomicAdd(a.counters + kCntNotBad, hist0);
+        if (hist1) atomicAdd(a.counters + kCntChimeric, hist1);
+        if (hist2) atomicAdd(a.counters + kCntNotCovered, hist2);
+        if (malformed) atomicAdd(a.counters + kCntMalformed, malformed);
     }
 }
 
-constexpr size_t kFusedSmemBytes = sizeof(uint2) * kSlabCap + sizeof(uint32_t) * kScratchWords * kFusedWarps + sizeof(TileSmem);
+constexpr size_t kFusedSmemBytes = kWarpSmemBytes * kFusedWarps;
 
 // FromReport path: bad regions are given, only type_of_read (editor/mod.rs:85-100) runs. One thread
 // takes 16 consecutive reads so it owns one 32-bit word of the 2-bit bitmap.
