@@ -193,7 +193,8 @@ int intern_read(yb_ctx *c, const char *id, size_t n, bool *is_new, uint32_t *idx
     return YB_OK;
 }
 
-inline void add_row(yb::RowStats *rs, uint64_t k) {
+inline void add_row(yb::RowStats *rs, uint64_t k, uint64_t len) {
+    if (len > yb::kPackedMaxLen) rs->n_wide += 1;
     const uint64_t bp = yb::big_pairs_for_row(k);
     if (bp) {
         rs->n_big += 1;
@@ -215,7 +216,7 @@ int freeze(yb_ctx *c) {
             if (c->b_len[r] > yb::kMaxLength) return c->fail(YB_ERR_TOO_LARGE, "read %u is longer than 2^31-1 bases", r);
             const uint32_t k = c->b_rowptr[r + 1] - c->b_rowptr[r];
             mk = std::max(mk, k);
-            add_row(&rs, k);
+            add_row(&rs, k, c->b_len[r]);
         }
         c->n_reads = n;
         c->n_iv = n ? c->b_rowptr[n] - c->b_rowptr[0] : 0;
@@ -237,7 +238,7 @@ int freeze(yb_ctx *c) {
     yb::RowStats rs;
     for (uint32_t r = 0; r < n; ++r) {
         mk = std::max(mk, rp[r + 1]);
-        add_row(&rs, rp[r + 1]);
+        add_row(&rs, rp[r + 1], c->length[r]);
         rp[r + 1] += rp[r];
     }
     std::vector<uint32_t> cur(rp, rp + n);
@@ -464,7 +465,7 @@ int yb_add_csr(yb_ctx *c, const uint32_t *rowptr, const uint32_t *iv, const uint
             if (length[r] > yb::kMaxLength) return c->fail(YB_ERR_TOO_LARGE, "read %u is longer than 2^31-1 bases", r);
             const uint32_t k = rowptr[r + 1] - rowptr[r];
             mk = std::max(mk, k);
-            add_row(&rs, k);
+            add_row(&rs, k, length[r]);
             c->h_rowptr.p[old_n + r + 1] = (uint32_t)(old_m + (rowptr[r + 1] - rowptr[0]));
             c->h_len.p[old_n + r] = length[r];
         }

@@ -1,5 +1,5 @@
 // pileup.cuh — internal interface between the C-ABI engine (engine.cu) and the sm_100a kernels
-// (pileup.cu). Not part of the public ABI.
+// (detect.cu). Not part of the public ABI.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,13 +16,15 @@ enum Counter : uint32_t {
     kCntChimeric = 1,
     kCntNotCovered = 2,
     kCntMalformed = 3,   // intervals violating 0 <= begin < end <= length
-    kCntTile = 4,        // dynamic tile scheduler
+    kCntTile = 4,        // dynamic tile scheduler of the packed (fast) pass
     kCntBigList = 5,     // rows with more than 256 intervals (big tier)
     kCntHugeBump = 6,    // bump allocator (in u32 keys) of the global-scratch tier
     kCntBigBump = 7,     // bump allocator (in pairs) of the big tier's side buffer
     kCntTierWarp = 8,    // reads taken by each tier
     kCntTierCta = 9,
     kCntTierHuge = 10,
+    kCntStage = 11,      // bump allocator (in pairs) of the bad-region staging buffer
+    kCntTileSlow = 12,   // dynamic tile scheduler of the generic (u32) pass
     kNumCounters = 16
 };
 
@@ -31,7 +33,11 @@ struct RowStats {
     uint64_t n_big = 0;      // rows with k > 256
     uint64_t big_pairs = 0;  // sum over them of k + 1 (side buffer of their bad regions)
     uint64_t huge_keys = 0;  // sum over rows beyond the shared-memory tier of next_pow2(2k)
+    uint64_t n_wide = 0;     // rows longer than kPackedMaxLen (positions do not fit 16 bits)
 };
+
+// Rows whose length is <= kPackedMaxLen are sorted as packed u16x2 keys (begin | end << 16).
+constexpr uint32_t kPackedMaxLen = 65534u;
 
 struct DetectArgs {
     // CSR input, resident in HBM
