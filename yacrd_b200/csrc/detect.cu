@@ -1,4 +1,4 @@
-// detect.cu — sm_100a kernels of the detect hot path (v4).
+// detect.cu — sm_100a kernels of the detect hot path (v5).
 //
 // Replaces, per read, FromOverlap::compute_bad_part (reference src/stack.rs:61-139) fused with
 // editor::type_of_read (src/editor/mod.rs:85-100). The reference sorts the intervals and sweeps them with
@@ -16,26 +16,26 @@
 //       [(0,U0) if U0 != 0] ++ [(D_t, U_t+1)] ++ [(D_last, len) if D_last != len]
 //   or [(0,len) if len != 0] when depth never exceeds c (tests/device_model.py is the executable form,
 //   fuzzed against the literal heap sweep in tests/test_device_model.py).
-//   Classification (editor/mod.rs:85-100): bad_len = len + sum(U) - sum(D) in wrapping u32;
-//   NotCovered iff (double)bad_len / (double)len > n (same IEEE divide, tested first); else Chimeric iff
-//   there is an interior gap <=> #U >= 2; else NotBad.
+//   Classification (editor/mod.rs:85-100) runs on the final bad-region list exactly as the reference does:
+//   bad_len = sum(end - begin) in wrapping u32; NotCovered iff (double)bad_len / (double)len > n (same IEEE
+//   divide, tested first); else Chimeric iff some region has begin != 0 && end != len; else NotBad.
 //
 // Kernels (all integer work; no tensor cores — there is no contraction on this path):
-//   plan_kernel      tile descriptors (binary search on rowptr[r] + 8r), list of big rows.
+//   scatter_kernel   every row -> its size class (G = 1,2,3,4,5,6,8,10,16 lanes x 16 keys; packed or wide) and
+//                    a 16-byte worklist record {row, first interval, k, len}; rows with k > 256 -> big list.
 //   big_kernel       rows with k > 256: one CTA per row, 2k event keys bitonic-sorted in shared memory (or in
-//                    a global slab beyond 16384 events); results parked in a side buffer.
-//   fused_kernel<1>  the fast pass. Warps pull tiles of consecutive rows from an atomic counter; one TMA
-//                    bulk copy (cp.async.bulk, SASS UBLKCP) stages the tile's interval slab in shared memory
-//                    while the rows are binned by size; sub-warp groups of G = 1..16 lanes sort one row each
-//                    in registers as PACKED u16x2 keys (begin | end << 16): one VIMNMX.U16x2 moves a begin
-//                    and an end through the same network, so both sorts cost one; crossings come from two
-//                    u32 compares per slot against a skewed shared-memory copy; the tile's bad regions go to
-//                    a bump-allocated staging segment (one atomic per tile, no inter-tile waiting).
-//   fused_kernel<0>  the same pass with two u32 key arrays, for the tiles that hold a read longer than
-//                    65534 bases or a big row.
-//   scan_tiles_kernel / finalize_kernel / bitmap_kernel
-//                    exclusive scan of the per-tile totals, segment copy staging -> ordered bad-region CSR
-//                    (+ gap_ptr fix-up), 2-bit class bitmap and class histogram.
+//                    a global slab beyond 16384 events).
+//   sort_kernel      persistent warps walk the worklist in batches of floor(32 / G) rows of ONE class, so a
+//                    batch fills the warp with equal-sized lane groups. Each row's interval slab is pulled into
+//                    shared memory by its own TMA bulk copy (cp.async.bulk, SASS UBLKCP; double-buffered: the
+//                    copies of batch i+2 are issued when batch i is done). A group sorts its row in registers as
+//                    PACKED u16x2 keys (begin | end << 16) — one VIMNMX.U16x2 moves a begin and an end through
+//                    the same network, so both sorts cost one — or as two u32 arrays when the read is longer
+//                    than 65534 bases. Crossings come from two carry-chain compares per slot against a
+//                    transposed shared-memory copy; the batch's bad regions go to a bump-allocated staging
+//                    segment (one atomic per batch, no waiting between warps).
+//   order_kernel     single pass over the rows: scan of the per-row counts (decoupled look-back over cheap,
+//                    uniform parts), staging -> ordered bad-region CSR, classification, 2-bit bitmap, histogram.
 #include "pileup.cuh"
 
 namespace yb {
@@ -81,86 +81,68 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // geometry
 // ------------------------------------------------------------------------------------------------
 constexpr int E = 16;                          // keys per lane per array in the register tier
-constexpr uint32_t kSmallMaxK = 256;           // register tier: rows with k <= 256 (G = 16 lanes x 16 keys)
-#ifndef YB_TILE_W
-#define YB_TILE_W 1024
-#endif
-constexpr uint32_t kTileW = YB_TILE_W;         // tile = rows whose weight rowptr[r] + 8r falls in one window
-constexpr uint32_t kReadW = 8;
-constexpr uint32_t kMaxTileReads = kTileW / kReadW;
-constexpr uint32_t kSlabCap = kTileW + kSmallMaxK + 64;  // intervals staged per tile (+ alignment slack per run)
-#ifndef YB_FUSED_WARPS
-#define YB_FUSED_WARPS 2
-#endif
-constexpr uint32_t kFusedWarps = YB_FUSED_WARPS;
-constexpr uint32_t kFusedThreads = kFusedWarps * 32;
+constexpr uint32_t kSmallMaxK = kRegisterTierMaxK;
+constexpr uint32_t kSortWarps = 2;             // warps per CTA of sort_kernel (warps never synchronise with each other)
+constexpr uint32_t kSortThreads = kSortWarps * 32;
+constexpr uint32_t kBufIntervals = 576;        // max over classes of floor(32/G) * (16 G + 2) row slots
 constexpr uint32_t kBigThreads = 512;
 constexpr uint32_t kBigSmemEvents = 16384;     // big_kernel: 64 KB of u32 event keys in shared memory
-constexpr uint32_t kSlowFlag = 0x80000000u;    // tile_desc.y: the tile goes to the generic (u32) pass
+constexpr uint32_t kPartRows = 1024;           // rows per CTA of scatter_kernel and order_kernel
+constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
+
+// Host-built table of the size classes (sizes are known from the row pointers at freeze time).
+struct ClassTab {
+    uint32_t entry_base[kNumClasses];     // where the class's records start in the worklist
+    uint32_t count[kNumClasses];          // rows in the class
+    uint32_t order[kNumClasses];          // classes in processing order (largest groups first)
+    uint32_t item_base[kNumClasses + 1];  // batches before the q-th class in processing order
+};
 
 // scratch carve-up
 struct Work {
-    uint4 *tile_desc;                // n_tiles + 1: {first row, rows | kSlowFlag, slab start (even), slab intervals (even)}
-    uint32_t *tile_base;             // n_tiles: where the tile's bad regions sit in `stage` (pairs)
-    uint32_t *tile_total;            // n_tiles: how many
-    uint32_t *tile_off;              // n_tiles + 1: exclusive scan of tile_total
-    uint2 *stage;                    // n_iv + n_reads pairs: bad regions in tile-completion order
+    uint4 *recs;                     // n_reads worklist records {row, first interval, k | class << 16 | valid, len}
+    uint32_t *soff;                  // n_reads: where the row's bad regions sit in `stage` (pairs)
+    uint2 *stage;                    // bad regions in batch-completion order, then the big rows' side buffer
+    uint32_t big_base;               // first pair of the big rows' side buffer inside `stage`
+    unsigned long long *status;      // order_kernel look-back: flag << 62 | value, one per part
+    uint32_t n_parts;
     uint32_t *big_list;              // rows with k > kSmallMaxK
-    uint32_t *big_off;               // their offset (in pairs) into big_gaps
-    uint32_t *big_cnt;               // their bad-region count
-    uint8_t *big_cls;                // their class
-    uint32_t *big_slot;              // n_reads: row -> index in big_list (valid for big rows only)
-    uint2 *big_gaps;                 // sum over big rows of (k + 1) pairs
+    uint32_t *big_off;               // their offset (in pairs) into the side buffer
     uint32_t *huge_keys;             // event keys of rows beyond the shared-memory tier
-    uint32_t n_tiles;
 };
 
-__host__ __device__ inline uint32_t n_tiles_of(uint32_t n_reads, uint32_t n_iv) {
-    const uint64_t total = (uint64_t)n_iv + (uint64_t)kReadW * n_reads;
-    return (uint32_t)(total / kTileW) + 1u;
-}
-
 // ------------------------------------------------------------------------------------------------
-// plan_kernel
+// scatter_kernel: rows -> worklist records grouped by size class (CTA-aggregated cursors)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t tile_boundary(const DetectArgs &a, uint32_t t) {
-    // first row r in [0, n_reads] with rowptr[r] + 8 r >= t * kTileW
-    const uint64_t target = (uint64_t)t * kTileW;
-    uint32_t lo = 0, hi = a.n_reads;
-    while (lo < hi) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        const uint64_t wgt = (uint64_t)__ldg(a.rowptr + mid) + (uint64_t)kReadW * mid;
-        if (wgt < target) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-__global__ void __launch_bounds__(256) plan_kernel(DetectArgs a, Work w, int check_rows) {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    for (uint32_t t = tid; t < w.n_tiles; t += nthr) {
-        const uint32_t r0 = tile_boundary(a, t), r1 = t + 1 == w.n_tiles ? a.n_reads : tile_boundary(a, t + 1);
-        const uint32_t p0 = __ldg(a.rowptr + r0), p1 = __ldg(a.rowptr + r1);
-        const uint32_t cs = p0 & ~1u, ce_ = (p1 + 1u) & ~1u;
-        uint32_t slow = ce_ - cs > kSlabCap ? kSlowFlag : 0u;
-        if (check_rows) {  // a read too long for 16-bit positions, or a big row, sends the tile to the generic pass
-            for (uint32_t r = r0; r < r1 && !slow; ++r) {
-                const uint32_t k = __ldg(a.rowptr + r + 1) - __ldg(a.rowptr + r);
-                if (k > kSmallMaxK || __ldg(a.len + r) > kPackedMaxLen) slow = kSlowFlag;
-            }
-        }
-        w.tile_desc[t] = make_uint4(r0, (r1 - r0) | slow, cs, ce_ - cs);
-    }
-    if (a.max_k > kSmallMaxK) {
-        for (uint32_t r = tid; r < a.n_reads; r += nthr) {
-            const uint32_t k = __ldg(a.rowptr + r + 1) - __ldg(a.rowptr + r);
-            if (k > kSmallMaxK) {
-                const uint32_t j = atomicAdd(a.counters + kCntBigList, 1u);
-                w.big_list[j] = r;
-                w.big_off[j] = atomicAdd(a.counters + kCntBigBump, k + 1u);
-                w.big_slot[r] = j;
-            }
+__global__ void __launch_bounds__(kPartRows) scatter_kernel(DetectArgs a, Work w, ClassTab tab) {
+    __shared__ uint32_t s_cnt[kNumClasses], s_base[kNumClasses];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * kPartRows + tid;
+    if (tid < (uint32_t)kNumClasses) s_cnt[tid] = 0u;
+    if (tid == 0 && blockIdx.x < w.n_parts) w.status[blockIdx.x] = 0ull;
+    __syncthreads();
+    int cls = -2;
+    uint32_t p0 = 0, k = 0, len = 0;
+    if (r < a.n_reads) {
+        p0 = __ldg(a.rowptr + r);
+        k = __ldg(a.rowptr + r + 1) - p0;
+        len = __ldg(a.len + r);
+        cls = class_of_row(k, len);
+        if (cls < 0) {
+            const uint32_t j = atomicAdd(a.counters + kCntBigList, 1u);
+            w.big_list[j] = r;
+            w.big_off[j] = atomicAdd(a.counters + kCntBigBump, k + 1u);
         }
     }
+    const uint32_t peers = __match_any_sync(FULL, cls);
+    const uint32_t leader = __ffs(peers) - 1u, rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t wbase = 0;
+    if (cls >= 0 && lane == leader) wbase = atomicAdd(&s_cnt[cls], (uint32_t)__popc(peers));
+    wbase = __shfl_sync(FULL, wbase, leader);
+    __syncthreads();
+    if (tid < (uint32_t)kNumClasses && s_cnt[tid]) s_base[tid] = atomicAdd(a.counters + kCntClassCursor + tid, s_cnt[tid]);
+    __syncthreads();
+    if (cls >= 0)
+        w.recs[tab.entry_base[cls] + s_base[cls] + wbase + rank] = make_uint4(r, p0, k | ((uint32_t)cls << 16) | kRecValid, len);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -326,15 +308,18 @@ __global__ void __launch_bounds__(kBigThreads) big_kernel(DetectArgs a, Work w, 
             __syncthreads();
             ev = w.huge_keys + sh_off;
         }
-        cta_pileup(ev, n_pow2, a.iv + s, k, a.len[r], c, not_cov, reinterpret_cast<uint32_t *>(w.big_gaps + w.big_off[j]),
-                   w.big_cls + j, w.big_cnt + j, sh, a.counters);
+        cta_pileup(ev, n_pow2, a.iv + s, k, a.len[r], c, not_cov, reinterpret_cast<uint32_t *>(w.stage + w.big_base + w.big_off[j]),
+                   a.cls + r, a.gap_ptr + r, sh, a.counters);
+        if (threadIdx.x == 0) w.soff[r] = w.big_base + w.big_off[j];
         __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// register tier: G lanes per row (G = 1..16, per lane at run time), E = 16 keys per lane,
-// blocked layout (element = g*16 + t): shuffles only on the log2(G) outermost merge levels.
+// register tier: G lanes per row (one G per batch), E = 16 keys per lane, blocked layout (element =
+// g*16 + t): shuffles only on the ceil(log2 G) outermost merge levels. G need not be a power of two: the
+// network is the one for next_pow2(G) lanes whose missing top lanes hold +inf, and every exchange with a
+// missing lane is a no-op, so it is simply predicated off.
 // PK: a key register holds begin | end << 16 and the network runs on both halves at once (VIMNMX.U16x2).
 // ------------------------------------------------------------------------------------------------
 template <bool PK> __device__ __forceinline__ uint32_t kmin(uint32_t a, uint32_t b) { return PK ? __vminu2(a, b) : min(a, b); }
@@ -357,23 +342,21 @@ template <bool PK> __device__ __forceinline__ void sort16(uint32_t (&k)[E]) {
 #undef CE
 }
 
-// Sorts, for every group of G lanes, its 16*G keys (ascending in element order g*16 + t). G is a per-lane
-// run-time power of two (groups of different sizes share a warp, larger groups on lower lanes, every group
-// aligned to its size); gmax is the warp's largest G. One rolled loop serves every group size. A lane whose
-// group is smaller than the current level keeps its (sorted) keys: its exchanges are predicated off and the
-// in-lane half-cleaners leave a sorted sequence as it is.
-template <bool PK> __device__ __forceinline__ void sort_group(uint32_t (&key)[E], uint32_t G, uint32_t gmax) {
+// Sorts, for every group of G consecutive lanes, its 16*G keys (ascending in element order g*16 + t).
+// `g` is the lane's index inside its group; lanes outside any group pass g = 0, in_group = false.
+template <bool PK> __device__ __forceinline__ void sort_group(uint32_t (&key)[E], uint32_t G, uint32_t g, bool in_group) {
     sort16<PK>(key);
     const uint32_t lane = lane_id();
 #pragma unroll 1
-    for (uint32_t ls = 2; ls <= gmax; ls <<= 1) {
-        const bool on = ls <= G;
-        {   // flip: element e pairs with e ^ (16*ls - 1): partner lane ^ (ls-1), slot 15 - t
-            const bool lo_half = (lane & (ls >> 1)) == 0;
-            const bool pmin = on && lo_half, pmax = on && !lo_half;
+    for (uint32_t ls = 2; ls < 2u * G; ls <<= 1) {
+        {   // flip: element e pairs with e ^ (16*ls - 1): partner lane g ^ (ls-1), slot 15 - t
+            const uint32_t partner = g ^ (ls - 1u);
+            const bool ex = in_group && partner < G, lo_half = (g & (ls >> 1)) == 0;
+            const bool pmin = ex && lo_half, pmax = ex && !lo_half;
+            const uint32_t src = ex ? lane + partner - g : lane;
             uint32_t other[E];
 #pragma unroll
-            for (int t = 0; t < E; ++t) other[t] = __shfl_xor_sync(FULL, key[E - 1 - t], ls - 1);
+            for (int t = 0; t < E; ++t) other[t] = __shfl_sync(FULL, key[E - 1 - t], src);
 #pragma unroll
             for (int t = 0; t < E; ++t) {
                 if (pmin) key[t] = kmin<PK>(key[t], other[t]);
@@ -382,11 +365,13 @@ template <bool PK> __device__ __forceinline__ void sort_group(uint32_t (&key)[E]
         }
 #pragma unroll 1
         for (uint32_t j = ls >> 2; j > 0; j >>= 1) {  // half-cleaners on the lane bits
-            const bool lo_half = (lane & j) == 0;
-            const bool pmin = on && lo_half, pmax = on && !lo_half;
+            const uint32_t partner = g ^ j;
+            const bool ex = in_group && partner < G, lo_half = (g & j) == 0;
+            const bool pmin = ex && lo_half, pmax = ex && !lo_half;
+            const uint32_t src = ex ? lane + partner - g : lane;
 #pragma unroll
             for (int t = 0; t < E; ++t) {
-                const uint32_t o = __shfl_xor_sync(FULL, key[t], j);
+                const uint32_t o = __shfl_sync(FULL, key[t], src);
                 if (pmin) key[t] = kmin<PK>(key[t], o);
                 if (pmax) key[t] = kmax<PK>(key[t], o);
             }
@@ -400,24 +385,15 @@ template <bool PK> __device__ __forceinline__ void sort_group(uint32_t (&key)[E]
     }
 }
 
-constexpr uint32_t kScratchWords = 17u * 33u + 3u;  // 33 blocks of 16 keys at a 17-word pitch
+constexpr uint32_t kScrPitch = 33;
+constexpr uint32_t kScrWords = 16u * kScrPitch + 4u;  // T[t][lane] at scr[1 + 33 t + lane]; scr[0] stands for lane -1
 
-struct alignas(16) WarpSmem {  // one per warp: a warp runs its tiles on its own, no CTA-wide barrier anywhere
-    unsigned long long mbar;
-    uint32_t row[kMaxTileReads + 1];   // rowptr values of the tile's rows (row i = read r0 + i)
-    uint32_t len[kMaxTileReads];
-    uint32_t meta[kMaxTileReads];      // n_gaps | h << 30 | tail << 31; big rows: n_gaps
-    uint32_t goff[kMaxTileReads];      // exclusive scan of n_gaps inside the tile
-    uint16_t soff[kMaxTileReads];      // slab offset (in intervals) of the row's data
-    uint16_t nup[kMaxTileReads];       // up-crossings of the row; kRowDone: finished without the sort
-    uint8_t order[kMaxTileReads];      // rows grouped by size class, largest first
-    uint8_t cls[kMaxTileReads];
-    uint32_t scr[kScratchWords];
+struct alignas(16) WarpSmem {  // one per warp: a warp runs on its own, no CTA-wide barrier anywhere
+    unsigned long long mbar[2];
+    uint32_t scr[kScrWords];
 };
-constexpr uint16_t kRowDone = 0xFFFFu;
-static_assert(sizeof(WarpSmem) % 16 == 0, "slab must stay 16-byte aligned");
-constexpr size_t kWarpSmemBytes = sizeof(WarpSmem) + sizeof(uint2) * kSlabCap;
-static_assert(kMaxTileReads <= 128 && kMaxTileReads % 32 == 0, "row ids are u8; rows are walked 32 at a time");
+static_assert(sizeof(WarpSmem) % 16 == 0, "slabs must stay 16-byte aligned");
+constexpr size_t kWarpSmemBytes = sizeof(WarpSmem) + 2 * sizeof(uint2) * kBufIntervals;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -447,22 +423,43 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
-// TMA prefetch of a global range into L2 (the next tile's slab, while this tile is being sorted).
-__device__ __forceinline__ void tma_prefetch_l2(const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+
+// m = 2 m + (ev <= q): the compare is the carry of q - ev, pushed in with an add-with-carry (SASS: IADD3 + IMAD.X)
+__device__ __forceinline__ uint32_t push_le(uint32_t m, uint32_t ev, uint32_t q) {
+    uint32_t r;
+    asm("{\n.reg .u32 t;\nsub.cc.u32 t, %1, %2;\naddc.u32 %0, %3, %3;\n}" : "=r"(r) : "r"(q), "r"(ev), "r"(m));
+    return r;
 }
 
-// One batch of rows: lane p of the batch belongs to the group of G lanes that owns row i_row (valid lanes
-// only). Sorts the row's begins and ends, finds the crossings and leaves them, U0 D0 U1 D1 ..., in the row's
-// own slab slot; the row's up-crossing count goes to ws.nup.
-template <bool PK>
-__device__ __forceinline__ void process_batch(WarpSmem &ws, uint2 *slab, bool valid, uint32_t i_row, uint32_t G, uint32_t g,
-                                              uint32_t gmax, uint32_t c, uint32_t &malformed) {
+// Lane geometry of a batch of class G: rows_per_batch groups of G consecutive lanes.
+struct LaneGeo {
+    uint32_t G, rpb, j, g;  // lanes per row, rows per batch, this lane's row slot and index in the group
+    bool in_group;
+};
+__device__ __forceinline__ LaneGeo lane_geo(uint32_t cls) {
+    LaneGeo x;
+    const uint32_t gi = cls >= (uint32_t)kNumG ? cls - (uint32_t)kNumG : cls;
+    x.G = class_lanes((int)gi);
+    x.rpb = 32u / x.G;
     const uint32_t lane = lane_id();
-    const uint32_t k = valid ? ws.row[i_row + 1] - ws.row[i_row] : 0u;
-    const uint32_t len = valid ? ws.len[i_row] : 0u;
-    const uint32_t so = valid ? ws.soff[i_row] : 0u;
-    const uint2 *row = slab + so;
+    x.j = (lane * ((65536u + x.G - 1u) / x.G)) >> 16;  // lane / G for lane < 32
+    x.g = lane - x.j * x.G;
+    x.in_group = x.j < x.rpb;
+    if (!x.in_group) x.g = 0;
+    return x;
+}
+
+// One batch: every in-group lane holds its row's record (all G lanes of a group hold the same one). Sorts the
+// row's begins and ends, finds the crossings (U0 D0 U1 D1 ... written over the row's slab slot), turns them
+// into bad regions and appends the batch's regions to the staging buffer.
+template <bool PK>
+__device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w, WarpSmem &ws, uint2 *buf, const LaneGeo geo,
+                                              const uint4 rec, uint32_t c, uint32_t &malformed) {
+    const uint32_t lane = lane_id();
+    const uint32_t G = geo.G, g = geo.g;
+    const bool valid = geo.in_group && (rec.z & kRecValid);
+    const uint32_t k = valid ? (rec.z & 0xFFFFu) : 0u, len = rec.w;
+    uint2 *slot = buf + geo.j * (16u * G + 2u) + (rec.y & 1u);  // the row's data starts here
     // striped load (conflict-free); the initial arrangement is irrelevant to the sort
     uint32_t K0[E];             // PK: begin | end << 16; else begins
     uint32_t K1[PK ? 1 : E];    // else ends
@@ -472,7 +469,7 @@ __device__ __forceinline__ void process_batch(WarpSmem &ws, uint2 *slab, bool va
         const uint32_t e = (uint32_t)t * G + g;
         uint2 v = make_uint2(INF, INF);
         if (e < k) {
-            v = row[e];
+            v = slot[e];
             bad_iv |= !(v.x < v.y && v.y <= len);
         }
         if (PK) {
@@ -484,11 +481,11 @@ __device__ __forceinline__ void process_batch(WarpSmem &ws, uint2 *slab, bool va
     }
     malformed += bad_iv;
     if (PK) {
-        sort_group<PK>(K0, G, gmax);
+        sort_group<PK>(K0, G, g, geo.in_group);
     } else {
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the network sorts begins, then ends
-            sort_group<PK>(K0, G, gmax);
+            sort_group<PK>(K0, G, g, geo.in_group);
 #pragma unroll
             for (int t = 0; t < E; ++t) {
                 const uint32_t x = K0[t];
@@ -497,412 +494,286 @@ __device__ __forceinline__ void process_batch(WarpSmem &ws, uint2 *slab, bool va
             }
         }
     }
-    // skewed copy of the sorted ends (PK: of the packed keys; the compares below only look at the end half):
-    // 17-word pitch per 16-key block, lane l's block at 17 (l + 1): conflict-free for the blocked writers and
-    // for the shifted readers
-    uint32_t *q = ws.scr + 17u * (lane + 1u);
+    // transposed copy of the sorted ends (PK: of the packed keys; the compares only look at the end half):
+    // T[t][lane]; element 16 l + t - c - 1 is then T[(t - c - 1) & 15][l + ((t - c - 1) >> 4)], a warp-uniform
+    // offset from the lane's own column: conflict-free writes and reads, no per-element index arithmetic
+    uint32_t *T = ws.scr + 1u + lane;
     __syncwarp();
 #pragma unroll
-    for (int t = 0; t < E; ++t) q[t] = PK ? K0[t] : K1[PK ? 0 : t];
+    for (int t = 0; t < E; ++t) T[kScrPitch * t] = PK ? K0[t] : K1[PK ? 0 : t];
     __syncwarp();
-    // Ev[t] = E[16 g + t - c - 1], t = 0..16 (0 below the row's first end)
-    uint32_t Ev[E + 1];
-    if (c < 16u) {
-        // 18 consecutive words starting in the previous lane's block; the pitch hole sits at index c + 1
-        const uint32_t *wptr = q - 2u - c;
-        uint32_t W[E + 2];
-#pragma unroll
-        for (int t = 0; t < E + 2; ++t) W[t] = wptr[t];
-#pragma unroll
-        for (int t = 0; t < E + 1; ++t) Ev[t] = (uint32_t)t <= c ? (g == 0u ? 0u : W[t]) : W[t + 1];
-    } else {
-        const uint32_t *q0 = q - 17u * g;  // the group's first block
-#pragma unroll
-        for (int t = 0; t < E + 1; ++t) {
-            const int e = (int)(16u * g + t) - (int)min(c, 0x7FFFFFF0u) - 1;
-            Ev[t] = e < 0 ? 0u : q0[e + (e >> 4)];
-        }
-    }
-    uint32_t Knext = __shfl_down_sync(FULL, K0[0], 1);
-    if (g == G - 1u) Knext = INF;
-    // PK: (end_j <= begin_i)  <=>  key_j <= (begin_i << 16 | 0xFFFF) as plain u32
-    uint32_t um = 0, dm = 0;
+    // V1_t = (E[16g + t - c - 1] <= B_t), t = 0..16;  V0_t = (E[16g + t - c] <= B_t), t = 0..15.
+    // PK: (end_j <= begin_i)  <=>  key_j <= (begin_i << 16 | 0xFFFF) as plain u32.
+    // Built most-significant-first: m1 bit (16 - t) = V1_t, m0 bit (15 - t) = V0_t.
+    const uint32_t cc = min(c, 16u * 16u + 16u);  // beyond k every threshold behaves the same
+    uint32_t m1 = 0, m0 = 0;
     {
-        bool v1 = Ev[0] <= (PK ? __byte_perm(K0[0], FULL, 0x1044) : K0[0]);
+        uint32_t Knext = __shfl_down_sync(FULL, K0[0], 1);
+        if (g == G - 1u) Knext = INF;
 #pragma unroll
-        for (int t = 0; t < E; ++t) {
-            const uint32_t qt = PK ? __byte_perm(K0[t], FULL, 0x1044) : K0[t];
-            const uint32_t kn = t + 1 < E ? K0[(t + 1) % E] : Knext;
-            const uint32_t qn = PK ? __byte_perm(kn, FULL, 0x1044) : kn;
-            const bool v0 = Ev[t + 1] <= qt;
-            const bool v1n = Ev[t + 1] <= qn;
-            if (v1 && !v0) um |= 1u << t;
-            if (!v0 && v1n) dm |= 1u << t;
-            v1 = v1n;
+        for (int t = 0; t <= E; ++t) {
+            const int jr = t - (int)cc - 1;  // uniform
+            int col = jr >> 4;
+            if (cc >= 16u) col = max(col, -(int)lane - 1);  // stay inside scr; those elements are forced below
+            const uint32_t ev = T[(int)kScrPitch * (jr & 15) + col];
+            const uint32_t kt = t < E ? K0[t % E] : Knext;
+            const uint32_t q = PK ? __byte_perm(kt, FULL, 0x1044) : kt;
+            m1 = push_le(m1, ev, q);
+            if (t > 0) {
+                const uint32_t kp = K0[(t - 1) % E];
+                const uint32_t qp = PK ? __byte_perm(kp, FULL, 0x1044) : kp;
+                m0 = push_le(m0, ev, qp);
+            }
+        }
+        // elements below the row's first end are 0 (E[-1] = 0): V1_t true for 16g + t <= c, V0_t for 16g + t < c
+        const int z = (int)cc - 16 * (int)g;
+        if (z >= 0) {
+            const uint32_t zz = min((uint32_t)z, 16u);
+            m1 |= ((2u << zz) - 1u) << (16u - zz);
+            m0 |= ((1u << zz) - 1u) << (16u - zz);
         }
     }
+    // bit (15 - t): U at begin t = V1_t & !V0_t; D at end t = !V0_t & V1_{t+1}
+    uint32_t um = (m1 >> 1) & ~m0 & 0xFFFFu, dm = m1 & ~m0 & 0xFFFFu;
+    if (!valid) um = dm = 0;
     // ranks of this lane's crossings among the row's ups / downs (packed segmented scan over the group)
     const uint32_t mine = __popc(um) | (__popc(dm) << 16);
     uint32_t incl = mine;
 #pragma unroll 1
-    for (uint32_t off = 1; off < gmax; off <<= 1) {
+    for (uint32_t off = 1; off < G; off <<= 1) {
         const uint32_t o = __shfl_up_sync(FULL, incl, off);
         if (g >= off) incl += o;
     }
-    const uint32_t tot = __shfl_sync(FULL, incl, lane | (G - 1u));
+    const uint32_t tot = __shfl_sync(FULL, incl, min(lane - g + G - 1u, 31u));
     uint32_t ru = (incl - mine) & 0xFFFFu, rd = (incl - mine) >> 16;
     // crossings go back into the row's own slab slot (2k words, no longer needed): C[2j] = U_j, C[2j+1] = D_j
-    uint32_t *C = reinterpret_cast<uint32_t *>(slab + so);
-    if (um | dm) {
+    uint32_t *C = reinterpret_cast<uint32_t *>(slot);
+    if (PK) {
+        while (um) {  // sparse: a row has a handful of crossings
+            const int t = __clz(um) - 16;
+            um &= ~(0x8000u >> t);
+            C[2u * ru++] = T[(int)kScrPitch * t] & 0xFFFFu;
+        }
+        while (dm) {
+            const int t = __clz(dm) - 16;
+            dm &= ~(0x8000u >> t);
+            const int jr = t - (int)cc;
+            C[2u * rd++ + 1u] = T[(int)kScrPitch * (jr & 15) + (jr >> 4)] >> 16;
+        }
+    } else if (um | dm) {
 #pragma unroll
         for (int t = 0; t < E; ++t) {
-            if (um & (1u << t)) {
-                C[2u * ru] = PK ? (K0[t] & 0xFFFFu) : K0[t];
+            if (um & (0x8000u >> t)) {
+                C[2u * ru] = K0[t];
                 ++ru;
             }
-            if (dm & (1u << t)) {
-                C[2u * rd + 1u] = PK ? (Ev[t + 1] >> 16) : Ev[t + 1];
+            if (dm & (0x8000u >> t)) {
+                const int jr = t - (int)cc;
+                C[2u * rd + 1u] = T[(int)kScrPitch * (jr & 15) + (jr >> 4)];
                 ++rd;
             }
         }
     }
-    if (valid && g == 0u) ws.nup[i_row] = (uint16_t)(tot & 0xFFFFu);
-}
-
-// Everything a warp does for one tile. PK tiles hold only rows with k <= 256 and len <= kPackedMaxLen and
-// their slab is one contiguous range (plan_kernel checked), so the TMA copy is issued before the rows are
-// even looked at; the generic pass splits the slab around big rows first.
-template <bool PK>
-__device__ __forceinline__ void process_tile(const DetectArgs &a, const Work &w, WarpSmem &ws, uint2 *slab, uint32_t tile,
-                                             const uint4 d, uint32_t c, double not_cov, uint32_t &parity,
-                                             uint32_t &malformed, const uint4 *next_desc, bool have_next) {
-    const uint32_t lane = lane_id();
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t r0 = d.x, R = d.y & ~kSlowFlag;
-    if (R == 0) {  // empty window (inside a big row)
-        if (lane == 0) {
-            w.tile_base[tile] = 0u;
-            w.tile_total[tile] = 0u;
-        }
-        return;
-    }
-    if (PK && lane == 0) {
-        // generic-proxy accesses of the previous tile (crossings written into the slab) before the async-proxy writes
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&ws.mbar, d.w * 8u);
-        if (d.w) tma_load_1d(slab, a.iv + d.z, d.w * 8u, &ws.mbar);
-    }
-#pragma unroll 1
-    for (uint32_t i = lane; i <= R; i += 32u) ws.row[i] = __ldg(a.rowptr + r0 + i);
-#pragma unroll 1
-    for (uint32_t i = lane; i < R; i += 32u) ws.len[i] = __ldg(a.len + r0 + i);
     __syncwarp();
-    // ---- rows -> size classes (G = 1, 2, 4, 8, 16 lanes); trivial rows (k <= c: depth never exceeds c)
-    //      are finished here; big rows (k > 256) were finished by big_kernel ----
-    uint32_t cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0, cnt4 = 0;
-    uint32_t my_cls[kMaxTileReads / 32], my_rank[kMaxTileReads / 32];
-    bool any_big = false;
-#pragma unroll
-    for (uint32_t u = 0; u < kMaxTileReads / 32; ++u) {
-        const uint32_t i = u * 32u + lane;
-        uint32_t cl = 0xFFu;
-        if (u * 32u < R) {
-            if (i < R) {
-                const uint32_t k = ws.row[i + 1] - ws.row[i], len = ws.len[i];
-                if (!PK && k > kSmallMaxK) {
-                    cl = 0xFEu;
-                    ws.nup[i] = kRowDone;
-                } else if (k <= c) {
-                    const uint32_t ng = len != 0u;
-                    ws.meta[i] = ng | (ng << 30) | (ng << 31);
-                    ws.cls[i] = (uint8_t)classify(len, len, 0u, not_cov);
-                    ws.nup[i] = kRowDone;
-                    if (k) {  // still validate the intervals of a row that is not sorted
-                        const uint2 *gi = a.iv + ws.row[i];
-                        bool bad = false;
-#pragma unroll 1
-                        for (uint32_t j = 0; j < k; ++j) {
-                            const uint2 v = __ldg(gi + j);
-                            bad |= !(v.x < v.y && v.y <= len);
-                        }
-                        malformed += bad;
-                    }
-                } else {
-                    cl = k <= 16u ? 0u : (k <= 32u ? 1u : (k <= 64u ? 2u : (k <= 128u ? 3u : 4u)));
-                }
-            }
-            any_big |= cl == 0xFEu;
-            const uint32_t m0 = __ballot_sync(FULL, cl == 0u), m1 = __ballot_sync(FULL, cl == 1u);
-            const uint32_t m2 = __ballot_sync(FULL, cl == 2u), m3 = __ballot_sync(FULL, cl == 3u);
-            const uint32_t m4 = __ballot_sync(FULL, cl == 4u);
-            my_rank[u] = cl == 0u ? cnt0 + __popc(m0 & lt)
-                       : cl == 1u ? cnt1 + __popc(m1 & lt)
-                       : cl == 2u ? cnt2 + __popc(m2 & lt)
-                       : cl == 3u ? cnt3 + __popc(m3 & lt) : cnt4 + __popc(m4 & lt);
-            cnt0 += __popc(m0);
-            cnt1 += __popc(m1);
-            cnt2 += __popc(m2);
-            cnt3 += __popc(m3);
-            cnt4 += __popc(m4);
-        }
-        my_cls[u] = cl;
-    }
-    const bool tile_has_big = !PK && __any_sync(FULL, any_big);
-    // row order: class 4 (G = 16) first; lane position p of a row = lane base of its class + rank * G
-    const uint32_t rb4 = 0, rb3 = cnt4, rb2 = rb3 + cnt3, rb1 = rb2 + cnt2, rb0 = rb1 + cnt1;
-    const uint32_t lb3 = 16u * cnt4, lb2 = lb3 + 8u * cnt3, lb1 = lb2 + 4u * cnt2, lb0 = lb1 + 2u * cnt1;
-    const uint32_t lanes_total = lb0 + cnt0;
-#pragma unroll
-    for (uint32_t u = 0; u < kMaxTileReads / 32; ++u) {
-        const uint32_t i = u * 32u + lane, cl = my_cls[u];
-        if (cl < 5u) ws.order[(cl == 0u ? rb0 : cl == 1u ? rb1 : cl == 2u ? rb2 : cl == 3u ? rb3 : rb4) + my_rank[u]] = (uint8_t)i;
-        if (i < R && !tile_has_big) ws.soff[i] = (uint16_t)(ws.row[i] - (ws.row[0] & ~1u));
-    }
-    if (!PK) {
-        // ---- generic pass: stage the slab now, one TMA bulk copy per run of non-big rows ----
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (!tile_has_big) {
-                const uint32_t cs = ws.row[0] & ~1u, ce_ = (ws.row[R] + 1u) & ~1u, nb = (ce_ - cs) * 8u;
-                mbar_expect_tx(&ws.mbar, nb);
-                if (nb) tma_load_1d(slab, a.iv + cs, nb, &ws.mbar);
-            } else {
-                uint32_t bytes_total = 0;
-                for (int pass = 0; pass < 2; ++pass) {  // expect_tx must precede the copies
-                    uint32_t dd = 0, i = 0;
-                    while (i < R) {
-                        while (i < R && ws.row[i + 1] - ws.row[i] > kSmallMaxK) {
-                            ws.soff[i] = 0;
-                            ++i;
-                        }
-                        if (i >= R) break;
-                        uint32_t j = i;
-                        const uint32_t cs = ws.row[i] & ~1u;
-                        while (j < R && ws.row[j + 1] - ws.row[j] <= kSmallMaxK) {
-                            ws.soff[j] = (uint16_t)(dd + (ws.row[j] - cs));
-                            ++j;
-                        }
-                        const uint32_t ce_ = (ws.row[j] + 1u) & ~1u, nb = (ce_ - cs) * 8u;
-                        if (pass == 0) bytes_total += nb;
-                        else if (nb) tma_load_1d(slab + dd, a.iv + cs, nb, &ws.mbar);
-                        dd += ce_ - cs;
-                        i = j;
-                    }
-                    if (pass == 0) mbar_expect_tx(&ws.mbar, bytes_total);
-                }
-            }
-        }
-    }
-    __syncwarp();
-    mbar_wait(&ws.mbar, parity);
-    parity ^= 1u;
-    // ---- pass A: sort + crossings, 32 lanes of rows at a time ----
-    for (uint32_t p0 = 0; p0 < lanes_total; p0 += 32u) {
-        const uint32_t p = p0 + lane;
-        const bool valid = p < lanes_total;
-        const uint32_t cl = p < lb3 ? 4u : (p < lb2 ? 3u : (p < lb1 ? 2u : (p < lb0 ? 1u : 0u)));
-        const uint32_t G = 1u << cl;
-        const uint32_t rel = p - (cl == 4u ? 0u : cl == 3u ? lb3 : cl == 2u ? lb2 : cl == 1u ? lb1 : lb0);
-        const uint32_t rank = rel >> cl, g = rel & (G - 1u);
-        const uint32_t i_row = valid ? ws.order[(cl == 0u ? rb0 : cl == 1u ? rb1 : cl == 2u ? rb2 : cl == 3u ? rb3 : rb4) + rank] : 0u;
-        const uint32_t gmax = __shfl_sync(FULL, G, 0);  // classes are laid out largest first
-        process_batch<PK>(ws, slab, valid, i_row, G, g, gmax, c, malformed);
-    }
-    // the next tile's slab: HBM -> L2 while this tile finishes
-    if (PK && have_next && lane == 0) {
-        const uint4 dn = *next_desc;
-        if (!(dn.y & kSlowFlag) && dn.w) tma_prefetch_l2(a.iv + dn.z, dn.w * 8u);
-    }
-    if (tile_has_big) {
-        for (uint32_t i = lane; i < R; i += 32u)
-            if (ws.row[i + 1] - ws.row[i] > kSmallMaxK) {
-                const uint32_t j = w.big_slot[r0 + i];
-                ws.meta[i] = w.big_cnt[j];
-                ws.cls[i] = w.big_cls[j];
-            }
-    }
-    __syncwarp();
-    // ---- per row (one lane each): bad-region count, flags, class; exclusive scan inside the tile ----
-    uint32_t carry = 0;
-#pragma unroll 1
-    for (uint32_t i0 = 0; i0 < R; i0 += 32u) {
-        const uint32_t i = i0 + lane;
-        uint32_t ng = 0;
-        if (i < R) {
-            const uint32_t n_up = ws.nup[i];
-            if (n_up != kRowDone) {
-                const uint32_t len = ws.len[i];
-                const uint32_t *C = reinterpret_cast<const uint32_t *>(slab + ws.soff[i]);
-                uint32_t h, tail, bad = len;
-                if (n_up) {
-                    h = C[0] != 0u;
-                    tail = C[2u * n_up - 1u] != len;
-                    ng = n_up - 1u + h + tail;
-#pragma unroll 1
-                    for (uint32_t j = 0; j < n_up; ++j) bad += C[2u * j] - C[2u * j + 1u];
-                } else {
-                    ng = h = tail = len != 0u;
-                }
-                ws.meta[i] = ng | (h << 30) | (tail << 31);
-                ws.cls[i] = (uint8_t)classify(bad, len, n_up, not_cov);
-            } else {
-                ng = ws.meta[i] & 0x3FFFFFFFu;
-            }
-        }
-        const uint32_t incl = warp_incl_scan(ng);
-        if (i < R) ws.goff[i] = carry + incl - ng;
-        carry += __shfl_sync(FULL, incl, 31);
-    }
-    const uint32_t tile_total = carry;
-    uint32_t base = 0;
-    if (lane == 0) {
-        if (tile_total) base = atomicAdd(a.counters + kCntStage, tile_total);
-        w.tile_base[tile] = base;
-        w.tile_total[tile] = tile_total;
-    }
-    base = __shfl_sync(FULL, base, 0);
-    __syncwarp();
-    // ---- pass B: classes, in-tile offsets and the tile's bad regions (staging segment) ----
-    for (uint32_t i = lane; i < R; i += 32u) {
-        const uint32_t m = ws.meta[i], len = ws.len[i], k = ws.row[i + 1] - ws.row[i];
-        const uint32_t at = base + ws.goff[i];
-        a.gap_ptr[r0 + i] = ws.goff[i];
-        a.cls[r0 + i] = ws.cls[i];
-        if (!PK && k > kSmallMaxK) {
-            const uint32_t j = w.big_slot[r0 + i];
-            const uint2 *src = w.big_gaps + w.big_off[j];
-            for (uint32_t gq = 0; gq < m; ++gq) w.stage[at + gq] = src[gq];
+    // ---- bad regions of the row (every lane of the group derives the same numbers) ----
+    const uint32_t n_up = tot & 0xFFFFu;
+    uint32_t ng = 0, h = 0, tail = 0;
+    if (valid) {
+        if (n_up) {
+            h = C[0] != 0u;
+            tail = C[2u * n_up - 1u] != len;
+            ng = n_up - 1u + h + tail;
         } else {
-            const uint32_t ng = m & 0x3FFFFFFFu, h = (m >> 30) & 1u, tail = m >> 31;
-            const uint32_t *C = reinterpret_cast<const uint32_t *>(slab + ws.soff[i]);
-            for (uint32_t gq = 0; gq < ng; ++gq) {
-                const uint32_t f0 = 2u * gq, f1 = f0 + 1u;
-                uint2 o;
-                o.x = (f0 == 0u && h) ? 0u : C[f0 + 1u - 2u * h];
-                o.y = (f1 == 2u * ng - 1u && tail) ? len : C[f1 + 1u - 2u * h];
-                w.stage[at + gq] = o;
-            }
+            ng = h = tail = len != 0u;
         }
     }
-    __syncwarp();
+    const uint32_t inc = warp_incl_scan(g == 0u ? ng : 0u);
+    const uint32_t total = __shfl_sync(FULL, inc, 31);
+    uint32_t base = 0;
+    if (lane == 0 && total) base = atomicAdd(a.counters + kCntStage, total);
+    base = __shfl_sync(FULL, base, 0) + inc - ng;
+    if (valid) {
+        if (g == 0u) {
+            a.gap_ptr[rec.x] = ng;  // count for now; order_kernel turns it into the offset
+            w.soff[rec.x] = base;
+        }
+        for (uint32_t gq = g; gq < ng; gq += G) {
+            const uint32_t f0 = 2u * gq, f1 = f0 + 1u;
+            uint2 o;
+            o.x = (f0 == 0u && h) ? 0u : C[f0 + 1u - 2u * h];
+            o.y = (f1 == 2u * ng - 1u && tail) ? len : C[f1 + 1u - 2u * h];
+            w.stage[base + gq] = o;
+        }
+    }
 }
 
-template <bool PK>
-__global__ void __launch_bounds__(kFusedThreads) fused_kernel(DetectArgs a, Work w, uint32_t c, double not_cov) {
+// The item's records for this lane (the record of the row its group sorts) — a plain 16-byte load.
+__device__ __forceinline__ uint4 load_rec(const Work &w, const ClassTab &tab, uint32_t item, uint32_t n_items, uint32_t &q) {
+    uint4 rec = make_uint4(0, 0, 0, 0);
+    if (item >= n_items) return rec;
+    while (item >= tab.item_base[q + 1]) ++q;
+    const uint32_t cls = tab.order[q];
+    const LaneGeo geo = lane_geo(cls);
+    const uint32_t e = (item - tab.item_base[q]) * geo.rpb + geo.j;
+    if (geo.in_group && e < tab.count[cls]) rec = __ldg(w.recs + tab.entry_base[cls] + e);
+    rec.z = (rec.z & (kRecValid | 0xFFFFu)) | (cls << 16);
+    return rec;
+}
+
+// TMA copies of the batch's row slabs into `buf` (one per row, issued by the group's first lane).
+__device__ __forceinline__ void issue_batch(const DetectArgs &a, uint2 *buf, unsigned long long *bar, const uint4 rec) {
+    const LaneGeo geo = lane_geo((rec.z >> 16) & 0x7FFFu);
+    uint32_t bytes = 0, cs = 0;
+    if (geo.in_group && geo.g == 0u && (rec.z & kRecValid)) {
+        cs = rec.y & ~1u;
+        bytes = (((rec.y + (rec.z & 0xFFFFu) + 1u) & ~1u) - cs) * 8u;
+    }
+    const uint32_t total = warp_sum(bytes);
+    if (lane_id() == 0) mbar_expect_tx(bar, total);
+    __syncwarp();
+    if (bytes) tma_load_1d(buf + geo.j * (16u * geo.G + 2u), a.iv + cs, bytes, bar);
+}
+
+__global__ void __launch_bounds__(kSortThreads) sort_kernel(DetectArgs a, Work w, ClassTab tab, uint32_t c) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     WarpSmem &ws = *reinterpret_cast<WarpSmem *>(smem_raw + wid * kWarpSmemBytes);
-    uint2 *slab = reinterpret_cast<uint2 *>(smem_raw + wid * kWarpSmemBytes + sizeof(WarpSmem));
+    uint2 *buf0 = reinterpret_cast<uint2 *>(smem_raw + wid * kWarpSmemBytes + sizeof(WarpSmem));
     if (lane == 0) {
-        mbar_init(&ws.mbar, 1);
+        mbar_init(&ws.mbar[0], 1);
+        mbar_init(&ws.mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    uint32_t parity = 0, malformed = 0;
-    if (PK) {
-        // dynamic schedule; the next tile's index and descriptor are fetched while this tile is processed
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(a.counters + kCntTile, 1u);
-        tile = __shfl_sync(FULL, tile, 0);
-        uint4 d = make_uint4(0, 0, 0, 0);
-        if (tile < w.n_tiles) d = __ldg(w.tile_desc + tile);
-        while (tile < w.n_tiles) {
-            uint32_t nxt = 0;
-            if (lane == 0) nxt = atomicAdd(a.counters + kCntTile, 1u);
-            nxt = __shfl_sync(FULL, nxt, 0);
-            const bool have_next = nxt < w.n_tiles;
-            if (!(d.y & kSlowFlag))
-                process_tile<true>(a, w, ws, slab, tile, d, c, not_cov, parity, malformed, w.tile_desc + nxt, have_next);
-            tile = nxt;
-            if (have_next) d = __ldg(w.tile_desc + tile);
-        }
-    } else {
-        const uint32_t n_warps = gridDim.x * kFusedWarps;
-        for (uint32_t tile = blockIdx.x * kFusedWarps + wid; tile < w.n_tiles; tile += n_warps) {
-            const uint4 d = __ldg(w.tile_desc + tile);
-            if (d.y & kSlowFlag) process_tile<false>(a, w, ws, slab, tile, d, c, not_cov, parity, malformed, nullptr, false);
-        }
+    const uint32_t n_items = tab.item_base[kNumClasses];
+    const uint32_t n_warps = gridDim.x * kSortWarps;
+    uint32_t item = blockIdx.x * kSortWarps + wid, q = 0, malformed = 0;
+    // software pipeline: records of batch i+2 are loaded, the slabs of batch i+1 are in flight, batch i is sorted
+    uint4 rec0 = load_rec(w, tab, item, n_items, q);
+    uint4 rec1 = load_rec(w, tab, item + n_warps, n_items, q);
+    if (item < n_items) issue_batch(a, buf0, &ws.mbar[0], rec0);
+    if (item + n_warps < n_items) issue_batch(a, buf0 + kBufIntervals, &ws.mbar[1], rec1);
+    uint32_t b = 0, parity = 0;
+    for (; item < n_items; item += n_warps) {
+        const uint32_t item2 = item + 2u * n_warps;
+        const uint4 rec2 = load_rec(w, tab, item2, n_items, q);
+        uint2 *buf = buf0 + b * kBufIntervals;
+        mbar_wait(&ws.mbar[b], parity);
+        const uint32_t cls = (rec0.z >> 16) & 0x7FFFu;
+        const LaneGeo geo = lane_geo(cls);
+        if (cls < (uint32_t)kNumG) process_batch<true>(a, w, ws, buf, geo, rec0, c, malformed);
+        else process_batch<false>(a, w, ws, buf, geo, rec0, c, malformed);
+        // generic-proxy accesses of this batch (crossings written into the slab) before the async-proxy refill
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (item2 < n_items) issue_batch(a, buf, &ws.mbar[b], rec2);
+        rec0 = rec1;
+        rec1 = rec2;
+        parity ^= b;
+        b ^= 1u;
     }
     malformed = warp_sum(malformed);
     if (lane == 0 && malformed) atomicAdd(a.counters + kCntMalformed, malformed);
 }
 
-constexpr size_t kFusedSmemBytes = kWarpSmemBytes * kFusedWarps;
+constexpr size_t kSortSmemBytes = kWarpSmemBytes * kSortWarps;
 
 // ------------------------------------------------------------------------------------------------
-// ordering pass: per-tile totals -> tile offsets -> ordered bad-region CSR, bitmap, histogram
+// order_kernel: counts -> offsets (single-pass scan, decoupled look-back over parts of 1024 rows), staging ->
+// ordered bad-region CSR, classification (editor/mod.rs:85-100), 2-bit bitmap, class histogram.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(DetectArgs a, Work w) {
-    __shared__ uint32_t sh[32];
-    const uint32_t tid = threadIdx.x, n = w.n_tiles;
-    const uint32_t per = (n + 1023u) / 1024u, beg = min(tid * per, n), end = min(beg + per, n);
-    uint32_t s = 0;
-    for (uint32_t i = beg; i < end; ++i) s += w.tile_total[i];
-    const uint32_t incl = warp_incl_scan(s);
-    if ((tid & 31u) == 31u) sh[tid >> 5] = incl;
+__global__ void __launch_bounds__(256) order_kernel(DetectArgs a, Work w, double not_cov) {
+    __shared__ uint32_t s_part, s_warp[8], s_prefix;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    if (tid == 0) s_part = atomicAdd(a.counters + kCntTicket, 1u);
     __syncthreads();
-    if (tid < 32u) {
-        const uint32_t v = sh[tid], iv = warp_incl_scan(v);
-        sh[tid] = iv - v;
-        if (tid == 31u) {
-            w.tile_off[n] = iv;
-            a.gap_ptr[a.n_reads] = iv;
+    const uint32_t part = s_part;
+    const uint32_t r = part * kPartRows + tid * 4u;
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    if (r + 4u <= a.n_reads) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(a.gap_ptr + r);
+        cnt[0] = v.x; cnt[1] = v.y; cnt[2] = v.z; cnt[3] = v.w;
+    } else {
+        for (uint32_t i = 0; r + i < a.n_reads; ++i) cnt[i] = a.gap_ptr[r + i];
+    }
+    const uint32_t mine = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+    const uint32_t incl = warp_incl_scan(mine);
+    if (lane == 31u) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t v = lane < 8u ? s_warp[lane] : 0u;
+        const uint32_t iv = warp_incl_scan(v);
+        if (lane < 8u) s_warp[lane] = iv - v;
+        const uint32_t total = __shfl_sync(FULL, iv, 7);
+        // decoupled look-back over the parts before this one (they started earlier: the ticket orders them)
+        volatile unsigned long long *st = w.status;
+        if (lane == 0) st[part] = ((part ? 1ull : 2ull) << 62) | total;
+        uint32_t excl = 0;
+        if (part) {
+            int look = (int)part - 1;
+            for (;;) {
+                const int idx = look - (int)lane;
+                unsigned long long sv = (2ull << 62);
+                if (idx >= 0) sv = st[idx];
+                const uint32_t flag = (uint32_t)(sv >> 62);
+                const uint32_t inval = __ballot_sync(FULL, flag == 0u);
+                const uint32_t incl_m = __ballot_sync(FULL, flag == 2u);
+                const uint32_t upto = incl_m ? ((2u << (__ffs(incl_m) - 1)) - 1u) : FULL;
+                if (inval & upto) continue;  // a needed predecessor has not published yet
+                excl += warp_sum(((1u << lane) & upto) ? (uint32_t)sv : 0u);
+                if (incl_m) break;
+                look -= 32;
+            }
+            if (lane == 0) st[part] = (2ull << 62) | (unsigned long long)(excl + total);
+        }
+        if (lane == 0) {
+            s_prefix = excl;
+            if (part == w.n_parts - 1u) a.gap_ptr[a.n_reads] = excl + total;
         }
     }
     __syncthreads();
-    uint32_t run = sh[tid >> 5] + incl - s;
-    for (uint32_t i = beg; i < end; ++i) {
-        w.tile_off[i] = run;
-        run += w.tile_total[i];
-    }
-}
-
-// One warp per tile: gap_ptr += tile offset; staging segment -> final position.
-__global__ void __launch_bounds__(256) finalize_kernel(DetectArgs a, Work w) {
-    const uint32_t lane = lane_id();
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t tile = warp; tile < w.n_tiles; tile += n_warps) {
-        const uint4 d = __ldg(w.tile_desc + tile);
-        const uint32_t r0 = d.x, R = d.y & ~kSlowFlag;
-        const uint32_t off = w.tile_off[tile], base = w.tile_base[tile], tot = w.tile_total[tile];
-        for (uint32_t i = lane; i < R; i += 32u) a.gap_ptr[r0 + i] += off;
-        for (uint32_t j = lane; j < tot; j += 32u) a.gaps[off + j] = w.stage[base + j];
-    }
-}
-
-// One thread per 16 reads = one 32-bit word of the 2-bit bitmap; class histogram.
-__global__ void __launch_bounds__(256) bitmap_kernel(const uint8_t *__restrict__ cls, uint32_t n, uint8_t *__restrict__ bitmap,
-                                                      uint32_t *counters) {
-    const uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * 16u;
-    uint32_t h0 = 0, h1 = 0, h2 = 0;
-    if (base < n) {
-        uint32_t wv[4];
-        if (base + 16u <= n) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(cls + base);
-            wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
-        } else {
-            wv[0] = wv[1] = wv[2] = wv[3] = 0u;
-            for (uint32_t i = 0; base + i < n; ++i) wv[i >> 2] |= (uint32_t)cls[base + i] << (8u * (i & 3u));
-            h0 -= 16u - (n - base);  // the zero padding is not NotBad
-        }
-        uint32_t bits = 0;
+    uint32_t gp = s_prefix + s_warp[wid] + incl - mine;
+    uint32_t bits = 0, h0 = 0, h1 = 0, h2 = 0;
+    uint32_t gpv[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint32_t cl = (wv[i >> 2] >> (8 * (i & 3))) & 3u;
-            bits |= cl << (2 * i);
+    for (uint32_t i = 0; i < 4; ++i) {
+        gpv[i] = gp;
+        if (r + i < a.n_reads) {
+            const uint32_t l = __ldg(a.len + r + i);
+            const uint2 *src = w.stage + w.soff[r + i];
+            uint32_t bad = 0, interior = 0;
+            for (uint32_t gq = 0; gq < cnt[i]; ++gq) {
+                const uint2 v = src[gq];
+                a.gaps[gp + gq] = v;
+                bad += v.y - v.x;
+                interior |= (v.x != 0u && v.y != l) ? 1u : 0u;
+            }
+            const uint32_t cl = classify(bad, l, interior ? 2u : 0u, not_cov);
+            a.cls[r + i] = (uint8_t)cl;
+            bits |= cl << (2u * i);
             h0 += cl == 0u;
             h1 += cl == 1u;
             h2 += cl == 2u;
         }
-        reinterpret_cast<uint32_t *>(bitmap)[base >> 4] = bits;
+        gp += cnt[i];
     }
+    if (r + 4u <= a.n_reads) {
+        *reinterpret_cast<uint4 *>(a.gap_ptr + r) = make_uint4(gpv[0], gpv[1], gpv[2], gpv[3]);
+    } else {
+        for (uint32_t i = 0; r + i < a.n_reads; ++i) a.gap_ptr[r + i] = gpv[i];
+    }
+    // 4 rows per thread = 8 bits; 4 consecutive threads make one 32-bit word of the bitmap (16 rows)
+    bits <<= 8u * (lane & 3u);
+    bits |= __shfl_xor_sync(FULL, bits, 1);
+    bits |= __shfl_xor_sync(FULL, bits, 2);
+    if ((lane & 3u) == 0u && r < a.n_reads) reinterpret_cast<uint32_t *>(a.bitmap)[r >> 4] = bits;
     h0 = warp_sum(h0);
     h1 = warp_sum(h1);
     h2 = warp_sum(h2);
-    if (lane_id() == 0) {
-        if (h0) atomicAdd(counters + kCntNotBad, h0);
-        if (h1) atomicAdd(counters + kCntChimeric, h1);
-        if (h2) atomicAdd(counters + kCntNotCovered, h2);
+    if (lane == 0) {
+        if (h0) atomicAdd(a.counters + kCntNotBad, h0);
+        if (h1) atomicAdd(a.counters + kCntChimeric, h1);
+        if (h2) atomicAdd(a.counters + kCntNotCovered, h2);
     }
 }
 
@@ -940,18 +811,14 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, uint64_t big
         off += align256(bytes);
         return p;
     };
-    w.n_tiles = n_tiles_of(a.n_reads, a.n_iv);
-    w.tile_desc = reinterpret_cast<uint4 *>(take(sizeof(uint4) * ((size_t)w.n_tiles + 1)));
-    w.tile_base = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)w.n_tiles + 1)));
-    w.tile_total = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)w.n_tiles + 1)));
-    w.tile_off = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)w.n_tiles + 2)));
-    w.stage = reinterpret_cast<uint2 *>(take(sizeof(uint2) * ((size_t)a.n_iv + a.n_reads + 1)));
+    w.n_parts = (a.n_reads + kPartRows - 1u) / kPartRows;
+    w.recs = reinterpret_cast<uint4 *>(take(sizeof(uint4) * ((size_t)a.n_reads + 1)));
+    w.soff = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)a.n_reads + 1)));
+    w.big_base = a.n_iv + a.n_reads + 1u;
+    w.stage = reinterpret_cast<uint2 *>(take(sizeof(uint2) * ((size_t)w.big_base + big_pairs + 1)));
+    w.status = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * ((size_t)w.n_parts + 1)));
     w.big_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.big_off = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
-    w.big_cnt = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
-    w.big_cls = reinterpret_cast<uint8_t *>(take(n_big + 1));
-    w.big_slot = reinterpret_cast<uint32_t *>(take(n_big ? sizeof(uint32_t) * ((size_t)a.n_reads + 1) : 4));
-    w.big_gaps = reinterpret_cast<uint2 *>(take(sizeof(uint2) * (big_pairs + 1)));
     w.huge_keys = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (huge_keys + 1)));
     *total = off;
     return w;
@@ -975,17 +842,15 @@ size_t detect_scratch_bytes(uint32_t n_reads, uint32_t n_iv, const RowStats &rs)
 }
 
 int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, cudaStream_t stream) {
-    static int n_sm = 0, occ_fast = 0, occ_slow = 0;
+    static int n_sm = 0, occ_sort = 0;
     if (!n_sm) {
         int dev = 0, sm = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return -1;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
         if (cudaFuncSetAttribute(big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBigSmemEvents * sizeof(uint32_t))) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmemBytes) != cudaSuccess) return -1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fast, fused_kernel<true>, kFusedThreads, kFusedSmemBytes) != cudaSuccess) return -1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_slow, fused_kernel<false>, kFusedThreads, kFusedSmemBytes) != cudaSuccess) return -1;
-        if (occ_fast < 1 || occ_slow < 1) return -1;
+        if (cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, sort_kernel, kSortThreads, kSortSmemBytes) != cudaSuccess) return -1;
+        if (occ_sort < 1) return -1;
         n_sm = sm;
     }
     int launches = 0;
@@ -997,46 +862,45 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     size_t total = 0;
     Work w = carve(a, a.rows.huge_keys, a.rows.n_big, a.rows.big_pairs, &total);
     if (total > a.scratch_bytes) return -1;
-    const uint32_t c = coverage;
-    const bool any_slow = a.rows.n_big || a.rows.n_wide;
-    const uint32_t plan_items = a.rows.n_big ? (a.n_reads > w.n_tiles ? a.n_reads : w.n_tiles) : w.n_tiles;
-    uint32_t plan_blocks = (plan_items + 255u) / 256u;
-    if (plan_blocks > (uint32_t)n_sm * 8u) plan_blocks = (uint32_t)n_sm * 8u;
-    plan_kernel<<<plan_blocks, 256, 0, stream>>>(a, w, any_slow ? 1 : 0);
+    // size classes: records grouped by class; batches ordered largest groups first (wide before packed)
+    ClassTab tab;
+    uint32_t at = 0;
+    for (int cl = 0; cl < kNumClasses; ++cl) {
+        tab.entry_base[cl] = at;
+        tab.count[cl] = a.rows.class_count[cl];
+        at += tab.count[cl];
+    }
+    uint32_t items = 0;
+    int q = 0;
+    for (int gi = kNumG - 1; gi >= 0; --gi) {
+        for (int wide = 1; wide >= 0; --wide) {
+            const int cl = gi + (wide ? kNumG : 0);
+            const uint32_t rpb = 32u / class_lanes(gi);
+            tab.order[q] = (uint32_t)cl;
+            tab.item_base[q] = items;
+            items += (tab.count[cl] + rpb - 1u) / rpb;
+            ++q;
+        }
+    }
+    tab.item_base[kNumClasses] = items;
+
+    scatter_kernel<<<w.n_parts, kPartRows, 0, stream>>>(a, w, tab);
     ++launches;
     if (a.rows.n_big) {
         uint32_t grid = (uint32_t)n_sm * 2u;
         if (grid > a.rows.n_big) grid = (uint32_t)a.rows.n_big;
-        big_kernel<<<grid, kBigThreads, kBigSmemEvents * sizeof(uint32_t), stream>>>(a, w, c, not_coverage);
+        big_kernel<<<grid, kBigThreads, kBigSmemEvents * sizeof(uint32_t), stream>>>(a, w, coverage, not_coverage);
         ++launches;
     }
-    {
-        uint32_t grid = (uint32_t)(n_sm * occ_fast);
-        const uint32_t want = (w.n_tiles + kFusedWarps - 1u) / kFusedWarps;
+    if (items) {
+        uint32_t grid = (uint32_t)(n_sm * occ_sort);
+        const uint32_t want = (items + kSortWarps - 1u) / kSortWarps;
         if (grid > want) grid = want;
-        fused_kernel<true><<<grid, kFusedThreads, kFusedSmemBytes, stream>>>(a, w, c, not_coverage);
+        sort_kernel<<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage);
         ++launches;
     }
-    if (any_slow) {
-        uint32_t grid = (uint32_t)(n_sm * occ_slow);
-        const uint32_t want = (w.n_tiles + kFusedWarps - 1u) / kFusedWarps;
-        if (grid > want) grid = want;
-        fused_kernel<false><<<grid, kFusedThreads, kFusedSmemBytes, stream>>>(a, w, c, not_coverage);
-        ++launches;
-    }
-    scan_tiles_kernel<<<1, 1024, 0, stream>>>(a, w);
+    order_kernel<<<w.n_parts, 256, 0, stream>>>(a, w, not_coverage);
     ++launches;
-    {
-        uint32_t blocks = (w.n_tiles + 7u) / 8u;
-        if (blocks > (uint32_t)n_sm * 16u) blocks = (uint32_t)n_sm * 16u;
-        finalize_kernel<<<blocks, 256, 0, stream>>>(a, w);
-        ++launches;
-    }
-    {
-        const uint32_t threads = (a.n_reads + 15u) / 16u;
-        bitmap_kernel<<<(threads + 255u) / 256u, 256, 0, stream>>>(a.cls, a.n_reads, a.bitmap, a.counters);
-        ++launches;
-    }
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
 }

@@ -195,6 +195,8 @@ int intern_read(yb_ctx *c, const char *id, size_t n, bool *is_new, uint32_t *idx
 
 inline void add_row(yb::RowStats *rs, uint64_t k, uint64_t len) {
     if (len > yb::kPackedMaxLen) rs->n_wide += 1;
+    const int cls = yb::class_of_row(k > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)k, len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)len);
+    if (cls >= 0) rs->class_count[cls] += 1;
     const uint64_t bp = yb::big_pairs_for_row(k);
     if (bp) {
         rs->n_big += 1;
