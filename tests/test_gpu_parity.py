@@ -206,8 +206,8 @@ def _random_csr(rng, n_reads, k_choices, len_choices):
 def test_fuzz_small_reads_every_register_tier(c):
     rng = random.Random(1000 + c)
     rowptr, iv, length = _random_csr(rng, 6000, [0, 1, 2, 3, 4, 7, 8, 9, 15, 16, 17, 31, 32, 33, 50, 63, 64, 65, 100,
-                                                 127, 128, 129, 200, 255, 256],
-                                     [1, 2, 3, 8, 20, 64, 1000, 250000, 2**31 - 1])
+                                                 127, 128, 129, 160, 161, 200, 255, 256, 257, 400, 512],
+                                     [1, 2, 3, 8, 20, 64, 1000, 65533, 65534, 65535, 65536, 250000, 2**31 - 1])
     for n in (0.4, 0.8):
         assert_same_as_oracle(rowptr, iv, length, c, n)
 

@@ -21,9 +21,9 @@
 //   divide, tested first); else Chimeric iff some region has begin != 0 && end != len; else NotBad.
 //
 // Kernels (all integer work; no tensor cores — there is no contraction on this path):
-//   scatter_kernel   every row -> its size class (G = 1,2,3,4,5,6,8,10,16 lanes x 16 keys; packed or wide) and
-//                    a 16-byte worklist record {row, first interval, k, len}; rows with k > 256 -> big list.
-//   big_kernel       rows with k > 256: one CTA per row, 2k event keys bitonic-sorted in shared memory (or in
+//   scatter_kernel   every row -> its size class (G = 1,2,3,4,5,6,8,10,16,32 lanes x 16 keys; packed or wide) and
+//                    a 16-byte worklist record {row, first interval, k, len}; rows with k > 512 -> big list.
+//   big_kernel       rows with k > 512: one CTA per row, 2k event keys bitonic-sorted in shared memory (or in
 //                    a global slab beyond 16384 events).
 //   sort_kernel      persistent warps walk the worklist in batches of floor(32 / G) rows of ONE class, so a
 //                    batch fills the warp with equal-sized lane groups. Each row's interval slab is pulled into
@@ -84,10 +84,14 @@ constexpr int E = 16;                          // keys per lane per array in the
 constexpr uint32_t kSmallMaxK = kRegisterTierMaxK;
 constexpr uint32_t kSortWarps = 2;             // warps per CTA of sort_kernel (warps never synchronise with each other)
 constexpr uint32_t kSortThreads = kSortWarps * 32;
+#ifndef YB_SORT_MIN_CTAS
+#define YB_SORT_MIN_CTAS 10
+#endif
 constexpr uint32_t kBufIntervals = 576;        // max over classes of floor(32/G) * (16 G + 2) row slots
 constexpr uint32_t kBigThreads = 512;
 constexpr uint32_t kBigSmemEvents = 16384;     // big_kernel: 64 KB of u32 event keys in shared memory
 constexpr uint32_t kPartRows = 1024;           // rows per CTA of scatter_kernel and order_kernel
+constexpr uint32_t kStageChunk = 1024;       // pairs a warp reserves in the staging buffer per atomic
 constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
 
 // Host-built table of the size classes (sizes are known from the row pointers at freeze time).
@@ -96,18 +100,20 @@ struct ClassTab {
     uint32_t count[kNumClasses];          // rows in the class
     uint32_t order[kNumClasses];          // classes in processing order (largest groups first)
     uint32_t item_base[kNumClasses + 1];  // batches before the q-th class in processing order
+    uint32_t lanes[kNumClasses];          // G: lanes per row
+    uint32_t rpb[kNumClasses];            // rows per batch = 32 / G
+    uint32_t inv[kNumClasses];            // ceil(65536 / G): x / G == (x * inv) >> 16 for x < 2048
 };
 
 // scratch carve-up
 struct Work {
     uint4 *recs;                     // n_reads worklist records {row, first interval, k | class << 16 | valid, len}
     uint32_t *soff;                  // n_reads: where the row's bad regions sit in `stage` (pairs)
-    uint2 *stage;                    // bad regions in batch-completion order, then the big rows' side buffer
-    uint32_t big_base;               // first pair of the big rows' side buffer inside `stage`
+    uint2 *stage;                    // bad regions in batch-completion order (warps reserve chunks with one atomic)
+    uint32_t stage_cap;              // pairs
     unsigned long long *status;      // order_kernel look-back: flag << 62 | value, one per part
     uint32_t n_parts;
     uint32_t *big_list;              // rows with k > kSmallMaxK
-    uint32_t *big_off;               // their offset (in pairs) into the side buffer
     uint32_t *huge_keys;             // event keys of rows beyond the shared-memory tier
 };
 
@@ -130,7 +136,6 @@ __global__ void __launch_bounds__(kPartRows) scatter_kernel(DetectArgs a, Work w
         if (cls < 0) {
             const uint32_t j = atomicAdd(a.counters + kCntBigList, 1u);
             w.big_list[j] = r;
-            w.big_off[j] = atomicAdd(a.counters + kCntBigBump, k + 1u);
         }
     }
     const uint32_t peers = __match_any_sync(FULL, cls);
@@ -296,21 +301,22 @@ __device__ void cta_pileup(uint32_t *ev, uint32_t n_pow2, const uint2 *__restric
 __global__ void __launch_bounds__(kBigThreads) big_kernel(DetectArgs a, Work w, uint32_t c, double not_cov) {
     extern __shared__ uint32_t ev_smem[];
     __shared__ uint32_t sh[160];
-    __shared__ uint32_t sh_off;
+    __shared__ uint32_t sh_off, sh_stage;
     const uint32_t n_big = a.counters[kCntBigList];
     for (uint32_t j = blockIdx.x; j < n_big; j += gridDim.x) {
         const uint32_t r = w.big_list[j];
         const uint32_t s = a.rowptr[r], k = a.rowptr[r + 1] - s;
         const uint32_t n_pow2 = (uint32_t)next_pow2_u64(2ull * k);
         uint32_t *ev = ev_smem;
-        if (n_pow2 > kBigSmemEvents) {  // keys live in a bump-allocated global slab
-            if (threadIdx.x == 0) sh_off = atomicAdd(a.counters + kCntHugeBump, n_pow2);
-            __syncthreads();
-            ev = w.huge_keys + sh_off;
+        if (threadIdx.x == 0) {  // room for the row's k + 1 possible bad regions
+            sh_stage = atomicAdd(a.counters + kCntStage, k + 1u);
+            w.soff[r] = sh_stage;
+            if (n_pow2 > kBigSmemEvents) sh_off = atomicAdd(a.counters + kCntHugeBump, n_pow2);  // keys in a global slab
         }
-        cta_pileup(ev, n_pow2, a.iv + s, k, a.len[r], c, not_cov, reinterpret_cast<uint32_t *>(w.stage + w.big_base + w.big_off[j]),
+        __syncthreads();
+        if (n_pow2 > kBigSmemEvents) ev = w.huge_keys + sh_off;
+        cta_pileup(ev, n_pow2, a.iv + s, k, a.len[r], c, not_cov, reinterpret_cast<uint32_t *>(w.stage + sh_stage),
                    a.cls + r, a.gap_ptr + r, sh, a.counters);
-        if (threadIdx.x == 0) w.soff[r] = w.big_base + w.big_off[j];
         __syncthreads();
     }
 }
@@ -436,13 +442,12 @@ struct LaneGeo {
     uint32_t G, rpb, j, g;  // lanes per row, rows per batch, this lane's row slot and index in the group
     bool in_group;
 };
-__device__ __forceinline__ LaneGeo lane_geo(uint32_t cls) {
+__device__ __forceinline__ LaneGeo lane_geo(const ClassTab &tab, uint32_t cls) {
     LaneGeo x;
-    const uint32_t gi = cls >= (uint32_t)kNumG ? cls - (uint32_t)kNumG : cls;
-    x.G = class_lanes((int)gi);
-    x.rpb = 32u / x.G;
+    x.G = tab.lanes[cls];
+    x.rpb = tab.rpb[cls];
     const uint32_t lane = lane_id();
-    x.j = (lane * ((65536u + x.G - 1u) / x.G)) >> 16;  // lane / G for lane < 32
+    x.j = (lane * tab.inv[cls]) >> 16;  // lane / G
     x.g = lane - x.j * x.G;
     x.in_group = x.j < x.rpb;
     if (!x.in_group) x.g = 0;
@@ -454,7 +459,7 @@ __device__ __forceinline__ LaneGeo lane_geo(uint32_t cls) {
 // into bad regions and appends the batch's regions to the staging buffer.
 template <bool PK>
 __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w, WarpSmem &ws, uint2 *buf, const LaneGeo geo,
-                                              const uint4 rec, uint32_t c, uint32_t &malformed) {
+                                              const uint4 rec, uint32_t c, uint32_t &malformed, uint2 &chunk) {
     const uint32_t lane = lane_id();
     const uint32_t G = geo.G, g = geo.g;
     const bool valid = geo.in_group && (rec.z & kRecValid);
@@ -505,7 +510,7 @@ __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w
     // V1_t = (E[16g + t - c - 1] <= B_t), t = 0..16;  V0_t = (E[16g + t - c] <= B_t), t = 0..15.
     // PK: (end_j <= begin_i)  <=>  key_j <= (begin_i << 16 | 0xFFFF) as plain u32.
     // Built most-significant-first: m1 bit (16 - t) = V1_t, m0 bit (15 - t) = V0_t.
-    const uint32_t cc = min(c, 16u * 16u + 16u);  // beyond k every threshold behaves the same
+    const uint32_t cc = min(c, 16u * 32u + 16u);  // beyond k every threshold behaves the same
     uint32_t m1 = 0, m0 = 0;
     {
         uint32_t Knext = __shfl_down_sync(FULL, K0[0], 1);
@@ -587,11 +592,25 @@ __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w
             ng = h = tail = len != 0u;
         }
     }
+    // staging: the warp owns a chunk of the staging buffer and refills it with one atomic when it runs out
     const uint32_t inc = warp_incl_scan(g == 0u ? ng : 0u);
     const uint32_t total = __shfl_sync(FULL, inc, 31);
-    uint32_t base = 0;
-    if (lane == 0 && total) base = atomicAdd(a.counters + kCntStage, total);
-    base = __shfl_sync(FULL, base, 0) + inc - ng;
+    uint32_t base;
+    if (total <= chunk.y - chunk.x) {
+        base = chunk.x;
+        chunk.x += total;
+    } else {
+        const bool direct = total >= kStageChunk / 4u;  // a large batch takes exactly what it needs
+        uint32_t got = 0;
+        if (lane == 0) got = atomicAdd(a.counters + kCntStage, direct ? total : kStageChunk);
+        base = __shfl_sync(FULL, got, 0);
+        if (!direct) chunk = make_uint2(base + total, base + kStageChunk);
+    }
+    base += inc - ng;
+    if (valid && base + ng > w.stage_cap) {  // cannot happen with the capacity the engine allocates; never write outside
+        if (g == 0u) atomicAdd(a.counters + kCntStageOverflow, 1u);
+        ng = 0;
+    }
     if (valid) {
         if (g == 0u) {
             a.gap_ptr[rec.x] = ng;  // count for now; order_kernel turns it into the offset
@@ -607,22 +626,24 @@ __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w
     }
 }
 
-// The item's records for this lane (the record of the row its group sorts) — a plain 16-byte load.
-__device__ __forceinline__ uint4 load_rec(const Work &w, const ClassTab &tab, uint32_t item, uint32_t n_items, uint32_t &q) {
+// The item's record for this lane (the record of the row its group sorts) — a plain 16-byte load that
+// nothing touches until the batch is issued, so it stays in flight behind the current batch.
+__device__ __forceinline__ uint4 load_rec(const Work &w, const ClassTab &tab, uint32_t item, uint32_t n_items, uint32_t &q, uint32_t &cls) {
     uint4 rec = make_uint4(0, 0, 0, 0);
+    cls = 0;
     if (item >= n_items) return rec;
     while (item >= tab.item_base[q + 1]) ++q;
-    const uint32_t cls = tab.order[q];
-    const LaneGeo geo = lane_geo(cls);
+    cls = tab.order[q];
+    const LaneGeo geo = lane_geo(tab, cls);
     const uint32_t e = (item - tab.item_base[q]) * geo.rpb + geo.j;
     if (geo.in_group && e < tab.count[cls]) rec = __ldg(w.recs + tab.entry_base[cls] + e);
-    rec.z = (rec.z & (kRecValid | 0xFFFFu)) | (cls << 16);
     return rec;
 }
 
 // TMA copies of the batch's row slabs into `buf` (one per row, issued by the group's first lane).
-__device__ __forceinline__ void issue_batch(const DetectArgs &a, uint2 *buf, unsigned long long *bar, const uint4 rec) {
-    const LaneGeo geo = lane_geo((rec.z >> 16) & 0x7FFFu);
+__device__ __forceinline__ void issue_batch(const DetectArgs &a, const ClassTab &tab, uint2 *buf, unsigned long long *bar,
+                                            const uint4 rec, uint32_t cls) {
+    const LaneGeo geo = lane_geo(tab, cls);
     uint32_t bytes = 0, cs = 0;
     if (geo.in_group && geo.g == 0u && (rec.z & kRecValid)) {
         cs = rec.y & ~1u;
@@ -634,7 +655,7 @@ __device__ __forceinline__ void issue_batch(const DetectArgs &a, uint2 *buf, uns
     if (bytes) tma_load_1d(buf + geo.j * (16u * geo.G + 2u), a.iv + cs, bytes, bar);
 }
 
-__global__ void __launch_bounds__(kSortThreads) sort_kernel(DetectArgs a, Work w, ClassTab tab, uint32_t c) {
+__global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(DetectArgs a, Work w, ClassTab tab, uint32_t c) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     WarpSmem &ws = *reinterpret_cast<WarpSmem *>(smem_raw + wid * kWarpSmemBytes);
@@ -649,26 +670,29 @@ __global__ void __launch_bounds__(kSortThreads) sort_kernel(DetectArgs a, Work w
     const uint32_t n_warps = gridDim.x * kSortWarps;
     uint32_t item = blockIdx.x * kSortWarps + wid, q = 0, malformed = 0;
     // software pipeline: records of batch i+2 are loaded, the slabs of batch i+1 are in flight, batch i is sorted
-    uint4 rec0 = load_rec(w, tab, item, n_items, q);
-    uint4 rec1 = load_rec(w, tab, item + n_warps, n_items, q);
-    if (item < n_items) issue_batch(a, buf0, &ws.mbar[0], rec0);
-    if (item + n_warps < n_items) issue_batch(a, buf0 + kBufIntervals, &ws.mbar[1], rec1);
+    uint32_t cls0, cls1, cls2;
+    uint4 rec0 = load_rec(w, tab, item, n_items, q, cls0);
+    uint4 rec1 = load_rec(w, tab, item + n_warps, n_items, q, cls1);
+    if (item < n_items) issue_batch(a, tab, buf0, &ws.mbar[0], rec0, cls0);
+    if (item + n_warps < n_items) issue_batch(a, tab, buf0 + kBufIntervals, &ws.mbar[1], rec1, cls1);
     uint32_t b = 0, parity = 0;
+    uint2 chunk = make_uint2(0, 0);  // [next free pair, end) of the warp's staging chunk
     for (; item < n_items; item += n_warps) {
         const uint32_t item2 = item + 2u * n_warps;
-        const uint4 rec2 = load_rec(w, tab, item2, n_items, q);
+        const uint4 rec2 = load_rec(w, tab, item2, n_items, q, cls2);
         uint2 *buf = buf0 + b * kBufIntervals;
         mbar_wait(&ws.mbar[b], parity);
-        const uint32_t cls = (rec0.z >> 16) & 0x7FFFu;
-        const LaneGeo geo = lane_geo(cls);
-        if (cls < (uint32_t)kNumG) process_batch<true>(a, w, ws, buf, geo, rec0, c, malformed);
-        else process_batch<false>(a, w, ws, buf, geo, rec0, c, malformed);
+        const LaneGeo geo = lane_geo(tab, cls0);
+        if (cls0 < (uint32_t)kNumG) process_batch<true>(a, w, ws, buf, geo, rec0, c, malformed, chunk);
+        else process_batch<false>(a, w, ws, buf, geo, rec0, c, malformed, chunk);
         // generic-proxy accesses of this batch (crossings written into the slab) before the async-proxy refill
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (item2 < n_items) issue_batch(a, buf, &ws.mbar[b], rec2);
+        if (item2 < n_items) issue_batch(a, tab, buf, &ws.mbar[b], rec2, cls2);
         rec0 = rec1;
         rec1 = rec2;
+        cls0 = cls1;
+        cls1 = cls2;
         parity ^= b;
         b ^= 1u;
     }
@@ -682,29 +706,24 @@ constexpr size_t kSortSmemBytes = kWarpSmemBytes * kSortWarps;
 // order_kernel: counts -> offsets (single-pass scan, decoupled look-back over parts of 1024 rows), staging ->
 // ordered bad-region CSR, classification (editor/mod.rs:85-100), 2-bit bitmap, class histogram.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) order_kernel(DetectArgs a, Work w, double not_cov) {
-    __shared__ uint32_t s_part, s_warp[8], s_prefix;
+__global__ void __launch_bounds__(kPartRows) order_kernel(DetectArgs a, Work w, double not_cov) {
+    __shared__ uint32_t s_part, s_warp[32], s_prefix;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     if (tid == 0) s_part = atomicAdd(a.counters + kCntTicket, 1u);
     __syncthreads();
     const uint32_t part = s_part;
-    const uint32_t r = part * kPartRows + tid * 4u;
-    uint32_t cnt[4] = {0, 0, 0, 0};
-    if (r + 4u <= a.n_reads) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(a.gap_ptr + r);
-        cnt[0] = v.x; cnt[1] = v.y; cnt[2] = v.z; cnt[3] = v.w;
-    } else {
-        for (uint32_t i = 0; r + i < a.n_reads; ++i) cnt[i] = a.gap_ptr[r + i];
-    }
-    const uint32_t mine = cnt[0] + cnt[1] + cnt[2] + cnt[3];
-    const uint32_t incl = warp_incl_scan(mine);
+    const uint32_t r = part * kPartRows + tid;
+    const bool live = r < a.n_reads;
+    const uint32_t cnt = live ? a.gap_ptr[r] : 0u;
+    const uint32_t l = live ? __ldg(a.len + r) : 0u;
+    const uint32_t incl = warp_incl_scan(cnt);
     if (lane == 31u) s_warp[wid] = incl;
     __syncthreads();
     if (wid == 0) {
-        const uint32_t v = lane < 8u ? s_warp[lane] : 0u;
+        const uint32_t v = s_warp[lane];
         const uint32_t iv = warp_incl_scan(v);
-        if (lane < 8u) s_warp[lane] = iv - v;
-        const uint32_t total = __shfl_sync(FULL, iv, 7);
+        s_warp[lane] = iv - v;
+        const uint32_t total = __shfl_sync(FULL, iv, 31);
         // decoupled look-back over the parts before this one (they started earlier: the ticket orders them)
         volatile unsigned long long *st = w.status;
         if (lane == 0) st[part] = ((part ? 1ull : 2ull) << 62) | total;
@@ -732,44 +751,30 @@ __global__ void __launch_bounds__(256) order_kernel(DetectArgs a, Work w, double
         }
     }
     __syncthreads();
-    uint32_t gp = s_prefix + s_warp[wid] + incl - mine;
-    uint32_t bits = 0, h0 = 0, h1 = 0, h2 = 0;
-    uint32_t gpv[4];
-#pragma unroll
-    for (uint32_t i = 0; i < 4; ++i) {
-        gpv[i] = gp;
-        if (r + i < a.n_reads) {
-            const uint32_t l = __ldg(a.len + r + i);
-            const uint2 *src = w.stage + w.soff[r + i];
-            uint32_t bad = 0, interior = 0;
-            for (uint32_t gq = 0; gq < cnt[i]; ++gq) {
-                const uint2 v = src[gq];
-                a.gaps[gp + gq] = v;
-                bad += v.y - v.x;
-                interior |= (v.x != 0u && v.y != l) ? 1u : 0u;
-            }
-            const uint32_t cl = classify(bad, l, interior ? 2u : 0u, not_cov);
-            a.cls[r + i] = (uint8_t)cl;
-            bits |= cl << (2u * i);
-            h0 += cl == 0u;
-            h1 += cl == 1u;
-            h2 += cl == 2u;
+    const uint32_t gp = s_prefix + s_warp[wid] + incl - cnt;
+    uint32_t cl = 0;
+    if (live) {
+        const uint2 *src = w.stage + w.soff[r];
+        uint32_t bad = 0, interior = 0;
+        for (uint32_t gq = 0; gq < cnt; ++gq) {
+            const uint2 v = src[gq];
+            a.gaps[gp + gq] = v;
+            bad += v.y - v.x;
+            interior |= (v.x != 0u && v.y != l) ? 1u : 0u;
         }
-        gp += cnt[i];
+        cl = classify(bad, l, interior ? 2u : 0u, not_cov);
+        a.cls[r] = (uint8_t)cl;
+        a.gap_ptr[r] = gp;
     }
-    if (r + 4u <= a.n_reads) {
-        *reinterpret_cast<uint4 *>(a.gap_ptr + r) = make_uint4(gpv[0], gpv[1], gpv[2], gpv[3]);
-    } else {
-        for (uint32_t i = 0; r + i < a.n_reads; ++i) a.gap_ptr[r + i] = gpv[i];
-    }
-    // 4 rows per thread = 8 bits; 4 consecutive threads make one 32-bit word of the bitmap (16 rows)
-    bits <<= 8u * (lane & 3u);
+    // 16 consecutive rows (half a warp) make one 32-bit word of the 2-bit bitmap
+    uint32_t bits = cl << (2u * (lane & 15u));
     bits |= __shfl_xor_sync(FULL, bits, 1);
     bits |= __shfl_xor_sync(FULL, bits, 2);
-    if ((lane & 3u) == 0u && r < a.n_reads) reinterpret_cast<uint32_t *>(a.bitmap)[r >> 4] = bits;
-    h0 = warp_sum(h0);
-    h1 = warp_sum(h1);
-    h2 = warp_sum(h2);
+    bits |= __shfl_xor_sync(FULL, bits, 4);
+    bits |= __shfl_xor_sync(FULL, bits, 8);
+    if ((lane & 15u) == 0u && live) reinterpret_cast<uint32_t *>(a.bitmap)[r >> 4] = bits;
+    const uint32_t h0 = __popc(__ballot_sync(FULL, live && cl == 0u)), h1 = __popc(__ballot_sync(FULL, cl == 1u));
+    const uint32_t h2 = __popc(__ballot_sync(FULL, cl == 2u));
     if (lane == 0) {
         if (h0) atomicAdd(a.counters + kCntNotBad, h0);
         if (h1) atomicAdd(a.counters + kCntChimeric, h1);
@@ -813,12 +818,15 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, uint64_t big
     };
     w.n_parts = (a.n_reads + kPartRows - 1u) / kPartRows;
     w.recs = reinterpret_cast<uint4 *>(take(sizeof(uint4) * ((size_t)a.n_reads + 1)));
+    (void)big_pairs;
     w.soff = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)a.n_reads + 1)));
-    w.big_base = a.n_iv + a.n_reads + 1u;
-    w.stage = reinterpret_cast<uint2 *>(take(sizeof(uint2) * ((size_t)w.big_base + big_pairs + 1)));
+    // worst case of the bad regions (k + 1 per row) + half of it for chunk remainders (a remainder is only dropped
+    // for a batch smaller than a quarter chunk, and a fresh chunk always holds at least two such batches)
+    const uint64_t cap = (uint64_t)a.n_iv + a.n_reads + ((uint64_t)a.n_iv + a.n_reads) / 2 + 4096ull * kStageChunk;  // + one open chunk per resident warp
+    w.stage_cap = cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cap;
+    w.stage = reinterpret_cast<uint2 *>(take(sizeof(uint2) * ((size_t)w.stage_cap + 1)));
     w.status = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * ((size_t)w.n_parts + 1)));
     w.big_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
-    w.big_off = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.huge_keys = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (huge_keys + 1)));
     *total = off;
     return w;
@@ -875,7 +883,10 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     for (int gi = kNumG - 1; gi >= 0; --gi) {
         for (int wide = 1; wide >= 0; --wide) {
             const int cl = gi + (wide ? kNumG : 0);
-            const uint32_t rpb = 32u / class_lanes(gi);
+            const uint32_t G = class_lanes(gi), rpb = 32u / G;
+            tab.lanes[cl] = G;
+            tab.rpb[cl] = rpb;
+            tab.inv[cl] = (65536u + G - 1u) / G;
             tab.order[q] = (uint32_t)cl;
             tab.item_base[q] = items;
             items += (tab.count[cl] + rpb - 1u) / rpb;
@@ -899,7 +910,7 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         sort_kernel<<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage);
         ++launches;
     }
-    order_kernel<<<w.n_parts, 256, 0, stream>>>(a, w, not_coverage);
+    order_kernel<<<w.n_parts, kPartRows, 0, stream>>>(a, w, not_coverage);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;

@@ -692,6 +692,8 @@ int yb_download(yb_ctx *c) {
         return c->fail(YB_ERR_MALFORMED_INTERVAL,
                        "%u interval(s) violate 0 <= begin < end <= length; the reference's result is undefined for them",
                        c->h_counters.p[yb::kCntMalformed]);
+    if (c->h_counters.p[yb::kCntStageOverflow])
+        return c->fail(YB_ERR_STATE, "internal error: bad-region staging buffer overflow (%u reads)", c->h_counters.p[yb::kCntStageOverflow]);
     c->n_gaps = c->h_gap_ptr.p[n];
     size_t d2h = sizeof(uint32_t) * (n + 1 + yb::kNumCounters) + n + c->bitmap_bytes();
     if (!c->from_report) {

@@ -17,7 +17,7 @@ enum Counter : uint32_t {
     kCntNotCovered = 2,
     kCntMalformed = 3,   // intervals violating 0 <= begin < end <= length
     kCntTile = 4,        // dynamic tile scheduler of the packed (fast) pass
-    kCntBigList = 5,     // rows with more than 256 intervals (big tier)
+    kCntBigList = 5,     // rows with more than 512 intervals (big tier)
     kCntHugeBump = 6,    // bump allocator (in u32 keys) of the global-scratch tier
     kCntBigBump = 7,     // bump allocator (in pairs) of the big tier's side buffer
     kCntTierWarp = 8,    // reads taken by each tier
@@ -25,6 +25,7 @@ enum Counter : uint32_t {
     kCntTierHuge = 10,
     kCntStage = 11,      // bump allocator (in pairs) of the bad-region staging buffer
     kCntTileSlow = 12,   // dynamic tile scheduler of the generic (u32) pass
+    kCntStageOverflow = 14,  // rows whose bad regions did not fit the staging buffer (must stay 0)
     kCntTicket = 13,     // order_kernel: dynamic part index (decoupled look-back needs in-order starts)
     kCntClassCursor = 16,  // kNumClasses cursors of the worklist scatter
     kNumCounters = 48
@@ -33,31 +34,31 @@ enum Counter : uint32_t {
 
 // Size classes of the register tier: a row with k intervals is sorted by G lanes x 16 keys, G the smallest
 // entry with 16 G >= k. Classes 0..kNumG-1 hold rows whose positions fit 16 bits (packed u16x2 keys),
-// kNumG..2 kNumG-1 the same sizes for longer reads (two u32 key arrays). Rows with k > 256 are "big".
-constexpr int kNumG = 9;
+// kNumG..2 kNumG-1 the same sizes for longer reads (two u32 key arrays). Rows with k > 512 are "big".
+constexpr int kNumG = 10;
 constexpr int kNumClasses = 2 * kNumG;
 __host__ __device__ inline uint32_t class_lanes(int gi) {
-    return gi == 0 ? 1u : gi == 1 ? 2u : gi == 2 ? 3u : gi == 3 ? 4u : gi == 4 ? 5u : gi == 5 ? 6u : gi == 6 ? 8u : gi == 7 ? 10u : 16u;
+    return gi == 0 ? 1u : gi == 1 ? 2u : gi == 2 ? 3u : gi == 3 ? 4u : gi == 4 ? 5u : gi == 5 ? 6u : gi == 6 ? 8u : gi == 7 ? 10u : gi == 8 ? 16u : 32u;
 }
 
 // Rows whose length is <= kPackedMaxLen are sorted as packed u16x2 keys (begin | end << 16).
 constexpr uint32_t kPackedMaxLen = 65534u;
-constexpr uint32_t kRegisterTierMaxK = 256u;
+constexpr uint32_t kRegisterTierMaxK = 512u;
 
-// Size class of a row, or -1 for a big row (k > 256).
+// Size class of a row, or -1 for a big row (k > 512).
 __host__ __device__ inline int class_of_row(uint32_t k, uint32_t len) {
     if (k > kRegisterTierMaxK) return -1;
-    const int gi = k <= 16u ? 0 : k <= 32u ? 1 : k <= 48u ? 2 : k <= 64u ? 3 : k <= 80u ? 4 : k <= 96u ? 5 : k <= 128u ? 6 : k <= 160u ? 7 : 8;
+    const int gi = k <= 16u ? 0 : k <= 32u ? 1 : k <= 48u ? 2 : k <= 64u ? 3 : k <= 80u ? 4 : k <= 96u ? 5 : k <= 128u ? 6 : k <= 160u ? 7 : k <= 256u ? 8 : 9;
     return gi + (len > kPackedMaxLen ? kNumG : 0);
 }
 
 // What the host knows about the rows at freeze time (sizes the scratch exactly).
 struct RowStats {
-    uint64_t n_big = 0;      // rows with k > 256
-    uint64_t big_pairs = 0;  // sum over them of k + 1 (side buffer of their bad regions)
+    uint64_t n_big = 0;      // rows with k > 512 (big tier)
+    uint64_t big_pairs = 0;  // sum over them of k + 1
     uint64_t huge_keys = 0;  // sum over rows beyond the shared-memory tier of next_pow2(2k)
     uint64_t n_wide = 0;     // rows longer than kPackedMaxLen (positions do not fit 16 bits)
-    uint32_t class_count[kNumClasses] = {};  // rows per size class (k <= 256)
+    uint32_t class_count[kNumClasses] = {};  // rows per size class (k <= 512)
 };
 
 
