@@ -90,7 +90,8 @@ constexpr uint32_t kSortThreads = kSortWarps * 32;
 constexpr uint32_t kBufIntervals = 576;        // max over classes of floor(32/G) * (16 G + 2) row slots
 constexpr uint32_t kBigThreads = 512;
 constexpr uint32_t kBigSmemEvents = 16384;     // big_kernel: 64 KB of u32 event keys in shared memory
-constexpr uint32_t kPartRows = 1024;           // rows per CTA of scatter_kernel and order_kernel
+constexpr uint32_t kScatterRows = 1024;        // rows per CTA of scatter_kernel
+constexpr uint32_t kPartShift = 8, kPartRows = 1u << kPartShift;  // rows per CTA of order_kernel
 constexpr uint32_t kStageChunk = 1024;       // pairs a warp reserves in the staging buffer per atomic
 constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
 
@@ -111,7 +112,8 @@ struct Work {
     uint32_t *soff;                  // n_reads: where the row's bad regions sit in `stage` (pairs)
     uint2 *stage;                    // bad regions in batch-completion order (warps reserve chunks with one atomic)
     uint32_t stage_cap;              // pairs
-    unsigned long long *status;      // order_kernel look-back: flag << 62 | value, one per part
+    uint32_t *part_total;            // bad regions of every part of kPartRows rows (RED by the sorting kernels)
+    uint32_t *part_prefix;           // exclusive scan of part_total
     uint32_t n_parts;
     uint32_t *big_list;              // rows with k > kSmallMaxK
     uint32_t *huge_keys;             // event keys of rows beyond the shared-memory tier
@@ -120,11 +122,12 @@ struct Work {
 // ------------------------------------------------------------------------------------------------
 // scatter_kernel: rows -> worklist records grouped by size class (CTA-aggregated cursors)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPartRows) scatter_kernel(DetectArgs a, Work w, ClassTab tab) {
+__global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Work w, ClassTab tab) {
     __shared__ uint32_t s_cnt[kNumClasses], s_base[kNumClasses];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * kPartRows + tid;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * kScatterRows + tid;
     if (tid < (uint32_t)kNumClasses) s_cnt[tid] = 0u;
-    if (tid == 0 && blockIdx.x < w.n_parts) w.status[blockIdx.x] = 0ull;
+    if (tid < kScatterRows / kPartRows && blockIdx.x * (kScatterRows / kPartRows) + tid < w.n_parts)
+        w.part_total[blockIdx.x * (kScatterRows / kPartRows) + tid] = 0u;
     __syncthreads();
     int cls = -2;
     uint32_t p0 = 0, k = 0, len = 0;
@@ -317,6 +320,7 @@ __global__ void __launch_bounds__(kBigThreads) big_kernel(DetectArgs a, Work w, 
         if (n_pow2 > kBigSmemEvents) ev = w.huge_keys + sh_off;
         cta_pileup(ev, n_pow2, a.iv + s, k, a.len[r], c, not_cov, reinterpret_cast<uint32_t *>(w.stage + sh_stage),
                    a.cls + r, a.gap_ptr + r, sh, a.counters);
+        if (threadIdx.x == 0 && a.gap_ptr[r]) atomicAdd(w.part_total + (r >> kPartShift), a.gap_ptr[r]);
         __syncthreads();
     }
 }
@@ -615,6 +619,7 @@ __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w
         if (g == 0u) {
             a.gap_ptr[rec.x] = ng;  // count for now; order_kernel turns it into the offset
             w.soff[rec.x] = base;
+            if (ng) atomicAdd(w.part_total + (rec.x >> kPartShift), ng);
         }
         for (uint32_t gq = g; gq < ng; gq += G) {
             const uint32_t f0 = 2u * gq, f1 = f0 + 1u;
@@ -703,60 +708,66 @@ __global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(De
 constexpr size_t kSortSmemBytes = kWarpSmemBytes * kSortWarps;
 
 // ------------------------------------------------------------------------------------------------
-// order_kernel: counts -> offsets (single-pass scan, decoupled look-back over parts of 1024 rows), staging ->
-// ordered bad-region CSR, classification (editor/mod.rs:85-100), 2-bit bitmap, class histogram.
+// ordering pass: the sorting kernels left, per row, a count and a staging offset, and per part of 256 rows the
+// part's total (RED). scan_parts_kernel scans the part totals; order_kernel turns counts into offsets inside
+// each part, moves the staged regions to their final place and classifies (editor/mod.rs:85-100).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPartRows) order_kernel(DetectArgs a, Work w, double not_cov) {
-    __shared__ uint32_t s_part, s_warp[32], s_prefix;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    if (tid == 0) s_part = atomicAdd(a.counters + kCntTicket, 1u);
+__global__ void __launch_bounds__(1024) scan_parts_kernel(DetectArgs a, Work w) {
+    __shared__ uint32_t sh[32];
+    const uint32_t tid = threadIdx.x, n = w.n_parts;
+    const uint32_t per = (n + 1023u) / 1024u, beg = min(tid * per, n), end = min(beg + per, n);
+    uint32_t s = 0;
+    for (uint32_t i = beg; i < end; ++i) s += w.part_total[i];
+    const uint32_t incl = warp_incl_scan(s);
+    if ((tid & 31u) == 31u) sh[tid >> 5] = incl;
     __syncthreads();
-    const uint32_t part = s_part;
-    const uint32_t r = part * kPartRows + tid;
+    if (tid < 32u) {
+        const uint32_t v = sh[tid], iv = warp_incl_scan(v);
+        sh[tid] = iv - v;
+        if (tid == 31u) a.gap_ptr[a.n_reads] = iv;
+    }
+    __syncthreads();
+    uint32_t run = sh[tid >> 5] + incl - s;
+    for (uint32_t i = beg; i < end; ++i) {
+        w.part_prefix[i] = run;
+        run += w.part_total[i];
+    }
+}
+
+__global__ void __launch_bounds__(kPartRows) order_kernel(DetectArgs a, Work w, double not_cov) {
+    __shared__ uint32_t s_warp[kPartRows / 32], s_hist[kPartRows / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t part = blockIdx.x, r = part * kPartRows + tid;
     const bool live = r < a.n_reads;
+    // everything the row needs is requested up front; the first two regions (most rows have <= 3) ride along
     const uint32_t cnt = live ? a.gap_ptr[r] : 0u;
     const uint32_t l = live ? __ldg(a.len + r) : 0u;
+    const uint2 *src = w.stage + (live ? w.soff[r] : 0u);
+    const uint32_t prefix = __ldg(w.part_prefix + part);
+    uint2 v0 = make_uint2(0, 0), v1 = make_uint2(0, 0);
+    if (cnt > 0u) v0 = src[0];
+    if (cnt > 1u) v1 = src[1];
     const uint32_t incl = warp_incl_scan(cnt);
     if (lane == 31u) s_warp[wid] = incl;
     __syncthreads();
-    if (wid == 0) {
-        const uint32_t v = s_warp[lane];
-        const uint32_t iv = warp_incl_scan(v);
-        s_warp[lane] = iv - v;
-        const uint32_t total = __shfl_sync(FULL, iv, 31);
-        // decoupled look-back over the parts before this one (they started earlier: the ticket orders them)
-        volatile unsigned long long *st = w.status;
-        if (lane == 0) st[part] = ((part ? 1ull : 2ull) << 62) | total;
-        uint32_t excl = 0;
-        if (part) {
-            int look = (int)part - 1;
-            for (;;) {
-                const int idx = look - (int)lane;
-                unsigned long long sv = (2ull << 62);
-                if (idx >= 0) sv = st[idx];
-                const uint32_t flag = (uint32_t)(sv >> 62);
-                const uint32_t inval = __ballot_sync(FULL, flag == 0u);
-                const uint32_t incl_m = __ballot_sync(FULL, flag == 2u);
-                const uint32_t upto = incl_m ? ((2u << (__ffs(incl_m) - 1)) - 1u) : FULL;
-                if (inval & upto) continue;  // a needed predecessor has not published yet
-                excl += warp_sum(((1u << lane) & upto) ? (uint32_t)sv : 0u);
-                if (incl_m) break;
-                look -= 32;
-            }
-            if (lane == 0) st[part] = (2ull << 62) | (unsigned long long)(excl + total);
-        }
-        if (lane == 0) {
-            s_prefix = excl;
-            if (part == w.n_parts - 1u) a.gap_ptr[a.n_reads] = excl + total;
-        }
-    }
-    __syncthreads();
-    const uint32_t gp = s_prefix + s_warp[wid] + incl - cnt;
+    uint32_t before = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < kPartRows / 32; ++q) before += q < wid ? s_warp[q] : 0u;
+    const uint32_t gp = prefix + before + incl - cnt;
     uint32_t cl = 0;
     if (live) {
-        const uint2 *src = w.stage + w.soff[r];
         uint32_t bad = 0, interior = 0;
-        for (uint32_t gq = 0; gq < cnt; ++gq) {
+        if (cnt > 0u) {
+            a.gaps[gp] = v0;
+            bad += v0.y - v0.x;
+            interior |= (v0.x != 0u && v0.y != l) ? 1u : 0u;
+        }
+        if (cnt > 1u) {
+            a.gaps[gp + 1u] = v1;
+            bad += v1.y - v1.x;
+            interior |= (v1.x != 0u && v1.y != l) ? 1u : 0u;
+        }
+        for (uint32_t gq = 2; gq < cnt; ++gq) {
             const uint2 v = src[gq];
             a.gaps[gp + gq] = v;
             bad += v.y - v.x;
@@ -773,12 +784,20 @@ __global__ void __launch_bounds__(kPartRows) order_kernel(DetectArgs a, Work w, 
     bits |= __shfl_xor_sync(FULL, bits, 4);
     bits |= __shfl_xor_sync(FULL, bits, 8);
     if ((lane & 15u) == 0u && live) reinterpret_cast<uint32_t *>(a.bitmap)[r >> 4] = bits;
-    const uint32_t h0 = __popc(__ballot_sync(FULL, live && cl == 0u)), h1 = __popc(__ballot_sync(FULL, cl == 1u));
-    const uint32_t h2 = __popc(__ballot_sync(FULL, cl == 2u));
-    if (lane == 0) {
-        if (h0) atomicAdd(a.counters + kCntNotBad, h0);
-        if (h1) atomicAdd(a.counters + kCntChimeric, h1);
-        if (h2) atomicAdd(a.counters + kCntNotCovered, h2);
+    // class histogram: one RED per class per CTA, spread over kHistSlots copies (same-address atomics serialise in L2)
+    const uint32_t h1 = __popc(__ballot_sync(FULL, cl == 1u)), h2 = __popc(__ballot_sync(FULL, cl == 2u));
+    if (lane == 0) s_hist[wid] = h1 | (h2 << 16);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t hs = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < kPartRows / 32; ++q) hs += s_hist[q];
+        const uint32_t n_live = min(kPartRows, a.n_reads - part * kPartRows);
+        uint32_t *slot = a.counters + kCntHist + 3u * (part % kHistSlots);
+        const uint32_t c1 = hs & 0xFFFFu, c2 = hs >> 16;
+        if (n_live - c1 - c2) atomicAdd(slot + 0, n_live - c1 - c2);
+        if (c1) atomicAdd(slot + 1, c1);
+        if (c2) atomicAdd(slot + 2, c2);
     }
 }
 
@@ -825,7 +844,8 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, uint64_t big
     const uint64_t cap = (uint64_t)a.n_iv + a.n_reads + ((uint64_t)a.n_iv + a.n_reads) / 2 + 4096ull * kStageChunk;  // + one open chunk per resident warp
     w.stage_cap = cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cap;
     w.stage = reinterpret_cast<uint2 *>(take(sizeof(uint2) * ((size_t)w.stage_cap + 1)));
-    w.status = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * ((size_t)w.n_parts + 1)));
+    w.part_total = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)w.n_parts + 8)));
+    w.part_prefix = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)w.n_parts + 8)));
     w.big_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.huge_keys = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (huge_keys + 1)));
     *total = off;
@@ -895,7 +915,7 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     }
     tab.item_base[kNumClasses] = items;
 
-    scatter_kernel<<<w.n_parts, kPartRows, 0, stream>>>(a, w, tab);
+    scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, tab);
     ++launches;
     if (a.rows.n_big) {
         uint32_t grid = (uint32_t)n_sm * 2u;
@@ -910,6 +930,8 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         sort_kernel<<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage);
         ++launches;
     }
+    scan_parts_kernel<<<1, 1024, 0, stream>>>(a, w);
+    ++launches;
     order_kernel<<<w.n_parts, kPartRows, 0, stream>>>(a, w, not_coverage);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;

@@ -708,9 +708,12 @@ int yb_download(yb_ctx *c) {
     c->stats.n_reads = n;
     c->stats.n_intervals = c->n_iv;
     c->stats.n_gaps = c->n_gaps;
-    c->stats.n_not_bad = c->h_counters.p[yb::kCntNotBad];
-    c->stats.n_chimeric = c->h_counters.p[yb::kCntChimeric];
-    c->stats.n_not_covered = c->h_counters.p[yb::kCntNotCovered];
+    uint64_t hist[3] = {c->h_counters.p[yb::kCntNotBad], c->h_counters.p[yb::kCntChimeric], c->h_counters.p[yb::kCntNotCovered]};
+    for (uint32_t sl = 0; sl < yb::kHistSlots; ++sl)  // the detect step stripes its histogram over kHistSlots copies
+        for (int t = 0; t < 3; ++t) hist[t] += c->h_counters.p[yb::kCntHist + 3 * sl + t];
+    c->stats.n_not_bad = hist[0];
+    c->stats.n_chimeric = hist[1];
+    c->stats.n_not_covered = hist[2];
     c->stats.max_intervals_per_read = c->max_k;
     c->downloaded = true;
     return YB_OK;

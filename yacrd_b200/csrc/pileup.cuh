@@ -28,8 +28,10 @@ enum Counter : uint32_t {
     kCntStageOverflow = 14,  // rows whose bad regions did not fit the staging buffer (must stay 0)
     kCntTicket = 13,     // order_kernel: dynamic part index (decoupled look-back needs in-order starts)
     kCntClassCursor = 16,  // kNumClasses cursors of the worklist scatter
-    kNumCounters = 48
+    kCntHist = 48,         // kHistSlots x {NotBad, Chimeric, NotCovered}: the detect step's class histogram, striped
+    kNumCounters = 48 + 3 * 32
 };
+constexpr uint32_t kHistSlots = 32;
 
 
 // Size classes of the register tier: a row with k intervals is sorted by G lanes x 16 keys, G the smallest
