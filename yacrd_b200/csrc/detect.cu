@@ -82,10 +82,13 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 // ------------------------------------------------------------------------------------------------
 constexpr int E = 16;                          // keys per lane per array in the register tier
 constexpr uint32_t kSmallMaxK = kRegisterTierMaxK;
-constexpr uint32_t kSortWarps = 2;             // warps per CTA of sort_kernel (warps never synchronise with each other)
+#ifndef YB_SORT_WARPS
+#define YB_SORT_WARPS 1
+#endif
+constexpr uint32_t kSortWarps = YB_SORT_WARPS;  // warps per CTA of sort_kernel (warps never synchronise with each other)
 constexpr uint32_t kSortThreads = kSortWarps * 32;
 #ifndef YB_SORT_MIN_CTAS
-#define YB_SORT_MIN_CTAS 10
+#define YB_SORT_MIN_CTAS (20 / YB_SORT_WARPS)
 #endif
 constexpr uint32_t kBufIntervals = 576;        // max over classes of floor(32/G) * (16 G + 2) row slots
 constexpr uint32_t kBigThreads = 512;
@@ -672,18 +675,25 @@ __global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(De
     }
     __syncwarp();
     const uint32_t n_items = tab.item_base[kNumClasses];
-    const uint32_t n_warps = gridDim.x * kSortWarps;
-    uint32_t item = blockIdx.x * kSortWarps + wid, q = 0, malformed = 0;
+    uint32_t q = 0, malformed = 0;
+    // Dynamic schedule (batches cost between 0.3 and 2 us): a warp draws batch indices from one counter, three
+    // batches ahead, so the atomic's latency hides behind a whole batch. Indices drawn by a warp only grow.
+    auto draw = [&]() {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(a.counters + kCntTile, 1u);
+        return __shfl_sync(FULL, t, 0);
+    };
+    uint32_t item = draw(), item1 = draw(), item2 = draw();
     // software pipeline: records of batch i+2 are loaded, the slabs of batch i+1 are in flight, batch i is sorted
     uint32_t cls0, cls1, cls2;
     uint4 rec0 = load_rec(w, tab, item, n_items, q, cls0);
-    uint4 rec1 = load_rec(w, tab, item + n_warps, n_items, q, cls1);
+    uint4 rec1 = load_rec(w, tab, item1, n_items, q, cls1);
     if (item < n_items) issue_batch(a, tab, buf0, &ws.mbar[0], rec0, cls0);
-    if (item + n_warps < n_items) issue_batch(a, tab, buf0 + kBufIntervals, &ws.mbar[1], rec1, cls1);
+    if (item1 < n_items) issue_batch(a, tab, buf0 + kBufIntervals, &ws.mbar[1], rec1, cls1);
     uint32_t b = 0, parity = 0;
     uint2 chunk = make_uint2(0, 0);  // [next free pair, end) of the warp's staging chunk
-    for (; item < n_items; item += n_warps) {
-        const uint32_t item2 = item + 2u * n_warps;
+    while (item < n_items) {
+        const uint32_t item3 = draw();
         const uint4 rec2 = load_rec(w, tab, item2, n_items, q, cls2);
         uint2 *buf = buf0 + b * kBufIntervals;
         mbar_wait(&ws.mbar[b], parity);
@@ -698,6 +708,9 @@ __global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(De
         rec1 = rec2;
         cls0 = cls1;
         cls1 = cls2;
+        item = item1;
+        item1 = item2;
+        item2 = item3;
         parity ^= b;
         b ^= 1u;
     }
