@@ -839,6 +839,53 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint32_t *__restric
     reinterpret_cast<uint32_t *>(bitmap)[base >> 4] = bits;
 }
 
+// ------------------------------------------------------------------------------------------------
+// row_stats_kernel (upload time): size-class histogram, big-row scratch needs, input sanity
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ len,
+                                                          uint32_t n_reads, DevRowStats *out) {
+    __shared__ uint32_t s_cnt[kNumClasses + 1], s_max, s_bad[3];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * 1024u + tid;
+    if (tid <= (uint32_t)kNumClasses) s_cnt[tid] = 0u;
+    if (tid < 3u) s_bad[tid] = 0u;
+    if (tid == 0) s_max = 0u;
+    __syncthreads();
+    int cls = -2;
+    uint32_t k = 0;
+    if (r < n_reads) {
+        const uint32_t p0 = __ldg(rowptr + r), p1 = __ldg(rowptr + r + 1), l = __ldg(len + r);
+        if (p1 < p0) {
+            atomicAdd(&s_bad[0], 1u);
+        } else {
+            k = p1 - p0;
+            cls = class_of_row(k, l);
+            if (cls < 0) {  // big row: rare, straight to the global sums
+                cls = kNumClasses;
+                atomicAdd(&out->big_pairs, (unsigned long long)k + 1ull);
+                const unsigned long long hk = next_pow2_u64(2ull * k);
+                if (hk > kBigSmemEvents) atomicAdd(&out->huge_keys, hk);
+            }
+            if (l > kPackedMaxLen) atomicAdd(&s_bad[2], 1u);
+        }
+        if (l > kMaxLength) atomicAdd(&s_bad[1], 1u);
+    }
+    const uint32_t peers = __match_any_sync(FULL, cls);
+    if (cls >= 0 && lane == (uint32_t)__ffs(peers) - 1u) atomicAdd(&s_cnt[cls], (uint32_t)__popc(peers));
+    uint32_t mk = k;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mk = max(mk, __shfl_xor_sync(FULL, mk, off));
+    if (lane == 0 && mk) atomicMax(&s_max, mk);
+    __syncthreads();
+    if (tid < (uint32_t)kNumClasses && s_cnt[tid]) atomicAdd(&out->class_count[tid], s_cnt[tid]);
+    if (tid == 0) {
+        if (s_cnt[kNumClasses]) atomicAdd(&out->n_big, s_cnt[kNumClasses]);
+        if (s_max) atomicMax(&out->max_k, s_max);
+        if (s_bad[0]) atomicAdd(&out->bad_rowptr, s_bad[0]);
+        if (s_bad[1]) atomicAdd(&out->bad_len, s_bad[1]);
+        if (s_bad[2]) atomicAdd(&out->n_wide, s_bad[2]);
+    }
+}
+
 Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, uint64_t big_pairs, size_t *total) {
     Work w;
     size_t off = 0;
@@ -866,6 +913,13 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, uint64_t big
 }
 
 }  // namespace
+
+int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream) {
+    if (cudaMemsetAsync(out, 0, sizeof(DevRowStats), stream) != cudaSuccess) return -1;
+    if (n_reads == 0) return 0;
+    row_stats_kernel<<<(n_reads + 1023u) / 1024u, 1024, 0, stream>>>(rowptr, len, n_reads, out);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
 
 uint64_t huge_keys_for_row(uint64_t k) {
     const uint64_t p = next_pow2_u64(2 * k);

@@ -118,6 +118,8 @@ struct yb_ctx {
     DeviceBuf<uint32_t> d_rowptr, d_len, d_gap_ptr, d_counters;
     DeviceBuf<uint2> d_iv, d_gaps;
     DeviceBuf<uint8_t> d_cls, d_bitmap, d_scratch;
+    DeviceBuf<yb::DevRowStats> d_rowstats;
+    PinnedBuf<yb::DevRowStats> h_rowstats;
     uint8_t *ext_bitmap = nullptr;  // yb_bind_device_bitmap
     size_t ext_bitmap_bytes = 0;
 
@@ -193,38 +195,15 @@ int intern_read(yb_ctx *c, const char *id, size_t n, bool *is_new, uint32_t *idx
     return YB_OK;
 }
 
-inline void add_row(yb::RowStats *rs, uint64_t k, uint64_t len) {
-    if (len > yb::kPackedMaxLen) rs->n_wide += 1;
-    const int cls = yb::class_of_row(k > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)k, len > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)len);
-    if (cls >= 0) rs->class_count[cls] += 1;
-    const uint64_t bp = yb::big_pairs_for_row(k);
-    if (bp) {
-        rs->n_big += 1;
-        rs->big_pairs += bp;
-        rs->huge_keys += yb::huge_keys_for_row(k);
-    }
-}
-
 // Freeze: counting sort of the arrival-order records by read -> CSR in pinned memory. Within a read the
 // arrival order is kept (the kernels sort anyway; yb_overlap shows arrival order like Reads2Ovl::overlap).
 int freeze(yb_ctx *c) {
     if (c->frozen) return YB_OK;
-    if (c->b_rowptr) {  // borrowed CSR: only derive the row statistics
+    if (c->b_rowptr) {  // borrowed CSR: nothing to build; the rows are inspected on the device at upload
         const uint32_t n = c->n_indexed;
-        uint32_t mk = 0;
-        yb::RowStats rs;
-        for (uint32_t r = 0; r < n; ++r) {
-            if (c->b_rowptr[r + 1] < c->b_rowptr[r]) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr is not monotone at read %u", r);
-            if (c->b_len[r] > yb::kMaxLength) return c->fail(YB_ERR_TOO_LARGE, "read %u is longer than 2^31-1 bases", r);
-            const uint32_t k = c->b_rowptr[r + 1] - c->b_rowptr[r];
-            mk = std::max(mk, k);
-            add_row(&rs, k, c->b_len[r]);
-        }
-        c->n_reads = n;
-        c->n_iv = n ? c->b_rowptr[n] - c->b_rowptr[0] : 0;
         if (n && c->b_rowptr[0] != 0) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr[0] must be 0");
-        c->max_k = mk;
-        c->rows = rs;
+        c->n_reads = n;
+        c->n_iv = n ? c->b_rowptr[n] : 0;
         c->frozen = true;
         return YB_OK;
     }
@@ -236,13 +215,7 @@ int freeze(yb_ctx *c) {
     uint32_t *rp = c->h_rowptr.p;
     memset(rp, 0, sizeof(uint32_t) * ((size_t)n + 1));
     for (size_t i = 0; i < m; ++i) rp[c->pending[i].read + 1]++;
-    uint32_t mk = 0;
-    yb::RowStats rs;
-    for (uint32_t r = 0; r < n; ++r) {
-        mk = std::max(mk, rp[r + 1]);
-        add_row(&rs, rp[r + 1], c->length[r]);
-        rp[r + 1] += rp[r];
-    }
+    for (uint32_t r = 0; r < n; ++r) rp[r + 1] += rp[r];
     std::vector<uint32_t> cur(rp, rp + n);
     for (size_t i = 0; i < m; ++i) {
         const yb::PendingRecord &p = c->pending[i];
@@ -255,8 +228,6 @@ int freeze(yb_ctx *c) {
     }
     c->n_reads = n;
     c->n_iv = (uint32_t)m;
-    c->max_k = mk;
-    c->rows = rs;
     c->frozen = true;
     return YB_OK;
 }
@@ -340,6 +311,8 @@ void yb_destroy(yb_ctx *c) {
     c->d_cls.release();
     c->d_bitmap.release();
     c->d_scratch.release();
+    c->d_rowstats.release();
+    c->h_rowstats.release();
     delete c;
 }
 
@@ -460,14 +433,9 @@ int yb_add_csr(yb_ctx *c, const uint32_t *rowptr, const uint32_t *iv, const uint
         } else if (!old_n) {
             c->h_rowptr.p[0] = 0;
         }
-        uint32_t mk = old_n ? c->max_k : 0;
-        yb::RowStats rs = old_n ? c->rows : yb::RowStats();
         for (uint32_t r = 0; r < n_reads; ++r) {
             if (rowptr[r + 1] < rowptr[r]) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr is not monotone at read %u", r);
             if (length[r] > yb::kMaxLength) return c->fail(YB_ERR_TOO_LARGE, "read %u is longer than 2^31-1 bases", r);
-            const uint32_t k = rowptr[r + 1] - rowptr[r];
-            mk = std::max(mk, k);
-            add_row(&rs, k, length[r]);
             c->h_rowptr.p[old_n + r + 1] = (uint32_t)(old_m + (rowptr[r + 1] - rowptr[0]));
             c->h_len.p[old_n + r] = length[r];
         }
@@ -476,8 +444,6 @@ int yb_add_csr(yb_ctx *c, const uint32_t *rowptr, const uint32_t *iv, const uint
         c->n_indexed = (uint32_t)tn;
         c->n_reads = (uint32_t)tn;
         c->n_iv = (uint32_t)(old_m + add_m);
-        c->max_k = mk;
-        c->rows = rs;
         c->invalidate();
         c->frozen = true;
         return YB_OK;
@@ -614,14 +580,41 @@ int yb_upload(yb_ctx *c) {
     if (!c->d_rowptr.reserve(n + 1) || !c->d_len.reserve(n + 1) || !c->d_iv.reserve(m + 2))
         return c->fail(YB_ERR_NOMEM, "device allocation failed (%zu reads, %zu intervals)", n, m);
     if (int rc = ensure_result_buffers(c)) return rc;
-    const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->rows);
-    if (!c->d_scratch.reserve(sb)) return c->fail(YB_ERR_NOMEM, "device scratch allocation failed (%zu bytes)", sb);
+    if (!c->d_rowstats.reserve(1) || !c->h_rowstats.reserve(1)) return c->fail(YB_ERR_NOMEM, "allocation failed");
     if (n) {
         YB_CUDA(c, cudaMemcpyAsync(c->d_rowptr.p, c->rowptr_host(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, c->stream));
         YB_CUDA(c, cudaMemcpyAsync(c->d_len.p, c->len_host(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
-        if (m) YB_CUDA(c, cudaMemcpyAsync(c->d_iv.p, c->iv_host(), sizeof(uint2) * m, cudaMemcpyHostToDevice, c->stream));
     }
+    // size classes, big-row scratch needs and input sanity come from one small kernel over rowptr / len; its
+    // 128-byte result crosses PCIe while the interval buffer is still on its way
+    const int sl = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->stream);
+    if (sl < 0) return c->cuda_fail(cudaGetLastError(), "row statistics kernel");
+    c->stats.kernel_launches += (uint64_t)sl;
+    YB_CUDA(c, cudaMemcpyAsync(c->h_rowstats.p, c->d_rowstats.p, sizeof(yb::DevRowStats), cudaMemcpyDeviceToHost, c->stream));
+    cudaEvent_t ev;
+    YB_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    YB_CUDA(c, cudaEventRecord(ev, c->stream));
+    if (n && m) YB_CUDA(c, cudaMemcpyAsync(c->d_iv.p, c->iv_host(), sizeof(uint2) * m, cudaMemcpyHostToDevice, c->stream));
+    const cudaError_t ee = cudaEventSynchronize(ev);
+    cudaEventDestroy(ev);
+    if (ee != cudaSuccess) return c->cuda_fail(ee, "cudaEventSynchronize");
+    {
+        const yb::DevRowStats &ds = *c->h_rowstats.p;
+        if (ds.bad_rowptr) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr is not monotone (%u reads)", ds.bad_rowptr);
+        if (ds.bad_len) return c->fail(YB_ERR_TOO_LARGE, "%u read(s) are longer than 2^31-1 bases", ds.bad_len);
+        yb::RowStats rs;
+        rs.n_big = ds.n_big;
+        rs.big_pairs = ds.big_pairs;
+        rs.huge_keys = ds.huge_keys;
+        rs.n_wide = ds.n_wide;
+        for (int q = 0; q < yb::kNumClasses; ++q) rs.class_count[q] = ds.class_count[q];
+        c->rows = rs;
+        c->max_k = ds.max_k;
+    }
+    const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->rows);
+    if (!c->d_scratch.reserve(sb)) return c->fail(YB_ERR_NOMEM, "device scratch allocation failed (%zu bytes)", sb);
     c->stats.h2d_bytes += sizeof(uint32_t) * (2 * n + 1) + sizeof(uint2) * m;
+    c->stats.d2h_bytes += sizeof(yb::DevRowStats);
     c->uploaded = true;
     c->computed = c->downloaded = false;
     return YB_OK;

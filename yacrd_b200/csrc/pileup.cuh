@@ -84,6 +84,19 @@ struct DetectArgs {
     size_t scratch_bytes;
 };
 
+// Row statistics gathered on the device at upload time (the host never loops over the rows of a bulk CSR).
+struct DevRowStats {
+    uint32_t class_count[kNumClasses];
+    uint32_t n_big, n_wide, max_k;
+    uint32_t bad_rowptr;           // rows with rowptr[r + 1] < rowptr[r]
+    uint32_t bad_len;              // rows longer than kMaxLength
+    uint32_t pad_;
+    unsigned long long big_pairs;  // sum over big rows of k + 1
+    unsigned long long huge_keys;  // sum over rows beyond the shared-memory tier of next_pow2(2k)
+};
+// Zeroes *out and fills it from the device-resident rowptr / len (one kernel on `stream`). Returns launches or -1.
+int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream);
+
 // Bytes of scratch launch_detect needs for a CSR of this shape.
 size_t detect_scratch_bytes(uint32_t n_reads, uint32_t n_iv, const RowStats &rs);
 // Per-row contributions to RowStats (the engine sums them over the rows at freeze time).
