@@ -57,10 +57,12 @@ typedef struct yb_opts {
     int32_t device;            /* CUDA ordinal; -1 = current device */
     uint32_t read_buffer_size; /* --read-buffer-size (cli.rs:57-59), used by yb_init_file; 0 = 8192 */
     uint32_t flags;            /* YB_FLAG_* */
-    uint32_t reserved;
+    uint32_t ingest_threads;   /* host threads of yb_init_file / yb_init_buffer; 0 = all cores (at most 32) */
 } yb_opts;
 
 #define YB_FLAG_KEEP_HOST_INTERVALS 1u /* keep arrival-order intervals so yb_overlap() works after upload */
+#define YB_FLAG_HOST_ONLY 2u /* producer side only (ingestion, interning, CSR freeze, Reads2Ovl queries): no device is
+                                touched; yb_upload / yb_compute_* fail with YB_ERR_CUDA. There is still no CPU pile-up. */
 
 typedef struct yb_stats {
     uint64_t n_reads;
@@ -193,6 +195,10 @@ uint64_t yb_synth_plan(const yb_synth_spec *spec, uint32_t *global_idx, uint32_t
 /* Pass 2: fill iv (pairs) for the rows planned by pass 1. threads <= 0: all cores. */
 int yb_synth_fill(const yb_synth_spec *spec, const uint32_t *global_idx, const uint32_t *rowptr,
                   const uint32_t *length, uint32_t n_local, uint32_t *iv, int threads);
+
+/* Synthetic PAF text for the ingestion bench (tools/bench_ingest.py): n_records records between pseudo-random pairs
+ * of n_reads reads. Returns the bytes written, or the bytes needed when out is NULL / cap is too small. */
+uint64_t yb_synth_paf(uint64_t seed, uint32_t n_reads, uint64_t n_records, char *out, uint64_t cap);
 
 #ifdef __cplusplus
 }

@@ -19,12 +19,13 @@ ERR_NAMES = {
     -9: "InvalidArgument", -10: "State", -11: "TooLarge", -12: "Cuda", -13: "NoMem",
 }
 NOT_BAD, CHIMERIC, NOT_COVERED = 0, 1, 2
+FLAG_KEEP_HOST_INTERVALS, FLAG_HOST_ONLY = 1, 2
 SYNTH_ONT, SYNTH_PACBIO_SKEW = 0, 1
 
 
 class YbOpts(C.Structure):
     _fields_ = [("device", C.c_int32), ("read_buffer_size", C.c_uint32), ("flags", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("ingest_threads", C.c_uint32)]
 
 
 class YbStats(C.Structure):
@@ -91,6 +92,7 @@ SIGNATURES = {
     "yb_synth_shard_of": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "yb_synth_count": (C.c_uint32, [C.POINTER(YbSynthSpec)]),
     "yb_synth_plan": (C.c_uint64, [C.POINTER(YbSynthSpec), _vp, _vp, _vp]),
+    "yb_synth_paf": (C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint64, _vp, C.c_uint64]),
     "yb_synth_fill": (C.c_int, [C.POINTER(YbSynthSpec), _vp, _vp, _vp, C.c_uint32, _vp, C.c_int]),
 }
 

@@ -58,9 +58,9 @@ def _view(ptr, n, dtype):
 class Context:
     """Owns one yb_ctx (one CUDA device + stream). Single-threaded, like the &mut self traits."""
 
-    def __init__(self, device=-1, read_buffer_size=8192, flags=0):
+    def __init__(self, device=-1, read_buffer_size=8192, flags=0, ingest_threads=0):
         self._L = N.lib()
-        opts = N.YbOpts(device, read_buffer_size, flags, 0)
+        opts = N.YbOpts(device, read_buffer_size, flags, ingest_threads)
         self._h = self._L.yb_create(C.byref(opts))
         if not self._h:
             raise N.YacrdError(-12, self._L.yb_create_error().decode())
@@ -198,8 +198,9 @@ def synth_csr(n_reads, mean_intervals, profile=N.SYNTH_ONT, seed=20261017, shard
 class FullMemory(Context):
     """reads2ovl::FullMemory (fullmemory.rs:29-99) + trait Reads2Ovl (reads2ovl/mod.rs:43-163)."""
 
-    def __init__(self, read_buffer_size=8192, device=-1):
-        super().__init__(device=device, read_buffer_size=read_buffer_size)
+    def __init__(self, read_buffer_size=8192, device=-1, ingest_threads=0, host_only=False):
+        super().__init__(device=device, read_buffer_size=read_buffer_size, ingest_threads=ingest_threads,
+                         flags=N.FLAG_HOST_ONLY if host_only else 0)
 
     def init(self, filename):  # mod.rs:44-81
         self._ck(self._L.yb_init_file(self._h, _b(filename)))

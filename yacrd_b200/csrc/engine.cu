@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <unordered_set>
@@ -30,14 +31,18 @@ thread_local std::string g_create_error;
 const char *const kTypeNames[3] = {"NotBad", "Chimeric", "NotCovered"};  // editor/mod.rs:51-58
 
 template <typename T>
-struct PinnedBuf {  // page-locked host buffer, grown geometrically
+struct PinnedBuf {  // page-locked host buffer, grown geometrically (plain memory in a host-only context)
     T *p = nullptr;
     size_t cap = 0;
+    bool plain = false;
     bool reserve(size_t n) {
         if (n <= cap) return true;
         release();
         size_t want = n + n / 8 + 16;
-        if (cudaMallocHost(reinterpret_cast<void **>(&p), want * sizeof(T)) != cudaSuccess) {
+        if (plain) {
+            p = static_cast<T *>(malloc(want * sizeof(T)));
+            if (!p) return false;
+        } else if (cudaMallocHost(reinterpret_cast<void **>(&p), want * sizeof(T)) != cudaSuccess) {
             cudaGetLastError();
             p = nullptr;
             cap = 0;
@@ -47,7 +52,10 @@ struct PinnedBuf {  // page-locked host buffer, grown geometrically
         return true;
     }
     void release() {
-        if (p) cudaFreeHost(p);
+        if (p) {
+            if (plain) free(p);
+            else cudaFreeHost(p);
+        }
         p = nullptr;
         cap = 0;
     }
@@ -95,6 +103,9 @@ struct yb_ctx {
     cudaStream_t stream = nullptr;
     uint32_t read_buffer_size = 8192;
     uint32_t flags = 0;
+    uint32_t ingest_threads = 0;
+    bool host_only = false;
+    bool bulk_frozen = false;  // the CSR came straight from the parallel ingester: `pending` does not hold it
     std::string error;
 
     // ---- host store (Reads2Ovl producer side) ----
@@ -186,7 +197,18 @@ int64_t find_read(const yb_ctx *c, const char *id, size_t n) {
     return i == yb::IdTable::kNone ? -1 : (int64_t)i;
 }
 
+// A CSR built by the parallel ingester goes back to arrival-order records when the caller keeps adding to it.
+void thaw(yb_ctx *c) {
+    if (!c->bulk_frozen) return;
+    const uint32_t *rp = c->h_rowptr.p;
+    c->pending.reserve((size_t)c->n_iv + 16);
+    for (uint32_t r = 0; r < c->n_reads; ++r)
+        for (uint32_t j = rp[r]; j < rp[r + 1]; ++j) c->pending.push_back({r, c->h_iv.p[j].x, c->h_iv.p[j].y});
+    c->bulk_frozen = false;
+}
+
 int intern_read(yb_ctx *c, const char *id, size_t n, bool *is_new, uint32_t *idx) {
+    thaw(c);
     if (c->indexed || c->from_report)
         return c->fail(YB_ERR_STATE, "this context holds bulk/report input; per-record adds are not allowed");
     if (c->ids.size() == 0xFFFFFFFEu) return c->fail(YB_ERR_TOO_LARGE, "too many reads");
@@ -250,6 +272,20 @@ const char *yb_create_error(void) { return g_create_error.c_str(); }
 const char *yb_last_error(const yb_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 
 yb_ctx *yb_create(const yb_opts *opts) {
+    if (opts && (opts->flags & YB_FLAG_HOST_ONLY)) {  // producer side only: no device, no compute
+        yb_ctx *c = new (std::nothrow) yb_ctx();
+        if (!c) {
+            g_create_error = "out of memory";
+            return nullptr;
+        }
+        c->host_only = true;
+        c->device = -1;
+        if (opts->read_buffer_size) c->read_buffer_size = opts->read_buffer_size;
+        c->flags = opts->flags;
+        c->ingest_threads = opts->ingest_threads;
+        c->h_rowptr.plain = c->h_len.plain = c->h_iv.plain = true;
+        return c;
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -277,6 +313,7 @@ yb_ctx *yb_create(const yb_opts *opts) {
     if (opts) {
         if (opts->read_buffer_size) c->read_buffer_size = opts->read_buffer_size;
         c->flags = opts->flags;
+        c->ingest_threads = opts->ingest_threads;
     }
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         cudaGetLastError();
@@ -289,6 +326,13 @@ yb_ctx *yb_create(const yb_opts *opts) {
 
 void yb_destroy(yb_ctx *c) {
     if (!c) return;
+    if (c->host_only) {
+        c->h_rowptr.release();
+        c->h_len.release();
+        c->h_iv.release();
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     if (c->stream) {
         cudaStreamSynchronize(c->stream);
@@ -325,8 +369,10 @@ static std::unordered_set<void *> g_host_plain;
 // (stack.rs:148-161 loops over batches) reuses them.
 int yb_reset(yb_ctx *c) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (!c->host_only) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+    }
     c->ids.clear();
     c->length.clear();
     c->pending.clear();
@@ -336,6 +382,7 @@ int yb_reset(yb_ctx *c) {
     c->n_reads = c->n_iv = c->max_k = c->n_gaps = 0;
     c->rows = yb::RowStats();
     c->from_report = false;
+    c->bulk_frozen = false;
     c->invalidate();
     return YB_OK;
 }
@@ -478,9 +525,38 @@ static bool add_sink(void *sink, const char *id, size_t id_len, uint32_t b, uint
     return yb_add_overlap_and_length(static_cast<yb_ctx *>(sink), id, id_len, b, e, len) == YB_OK;
 }
 
+static bool alloc_csr_sink(void *sink, size_t n_reads, size_t n_iv, uint32_t **rowptr, uint32_t **len, uint32_t **iv) {
+    yb_ctx *c = static_cast<yb_ctx *>(sink);
+    if (!c->h_rowptr.reserve(n_reads + 1) || !c->h_len.reserve(n_reads + 1) || !c->h_iv.reserve(n_iv + 1)) return false;
+    *rowptr = c->h_rowptr.p;
+    *len = c->h_len.p;
+    *iv = reinterpret_cast<uint32_t *>(c->h_iv.p);
+    return true;
+}
+
 int yb_init_buffer(yb_ctx *c, const char *text, size_t n_bytes, int format) {
     if (!c || (!text && n_bytes) || (format != 'p' && format != 'm')) return YB_ERR_INVALID_ARGUMENT;
     yb::IngestError err;
+    // An empty context and more than a few records: tokenize, intern and build the CSR on all host cores.
+    int threads = (int)c->ingest_threads;
+    if (threads == 0) {
+        threads = (int)std::thread::hardware_concurrency();
+        if (threads > 32) threads = 32;
+        if (n_bytes < (1u << 20)) threads = 1;
+    }
+    if (threads > 1 && c->total_reads() == 0 && !c->indexed && !c->from_report && c->pending.empty()) {
+        yb::BulkIds ids;
+        if (!yb::ingest_buffer_parallel(text, n_bytes, format, threads, alloc_csr_sink, c, &ids, &err))
+            return c->fail(err.code, "%s", err.message.c_str());
+        c->length = std::move(ids.length);
+        c->ids.adopt(std::move(ids.bytes), std::move(ids.off));
+        c->n_reads = ids.n_reads;
+        c->n_iv = (uint32_t)ids.n_iv;
+        c->invalidate();
+        c->frozen = true;
+        c->bulk_frozen = true;
+        return YB_OK;
+    }
     if (!yb::ingest_buffer(text, n_bytes, format, add_sink, c, &err)) {
         if (err.code == YB_ERR_NOMEM && !c->error.empty()) return YB_ERR_STATE;  // add refused (state)
         return c->fail(err.code, "%s", err.message.c_str());
@@ -572,6 +648,7 @@ int yb_overlap(yb_ctx *c, const char *id, size_t id_len, const uint32_t **iv_pai
 // ---- staged device API -------------------------------------------------------------------------------
 int yb_upload(yb_ctx *c) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (c->host_only) return c->fail(YB_ERR_CUDA, "host-only context: the detect path runs on a CUDA device only");
     if (c->from_report) return c->fail(YB_ERR_STATE, "context was loaded from a report; nothing to upload");
     YB_CUDA(c, cudaSetDevice(c->device));
     if (int rc = freeze(c)) return rc;
@@ -622,6 +699,7 @@ int yb_upload(yb_ctx *c) {
 
 int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *stream) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (c->host_only) return c->fail(YB_ERR_CUDA, "host-only context: the detect path runs on a CUDA device only");
     YB_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     c->coverage = coverage;
@@ -660,6 +738,7 @@ int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *s
 
 int yb_synchronize(yb_ctx *c) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (c->host_only) return YB_OK;
     YB_CUDA(c, cudaSetDevice(c->device));
     YB_CUDA(c, cudaStreamSynchronize(c->stream));
     return YB_OK;
@@ -883,6 +962,7 @@ int yb_write_report(yb_ctx *c, const char *path) {  // main.rs:62-84
 // ---- FromReport (stack.rs:176-257) -------------------------------------------------------------------
 int yb_init_report_buffer(yb_ctx *c, const char *text, size_t n_bytes) {
     if (!c || (!text && n_bytes)) return YB_ERR_INVALID_ARGUMENT;
+    if (c->host_only) return c->fail(YB_ERR_CUDA, "host-only context: reports are classified on a CUDA device only");
     if (c->total_reads() || c->from_report) return c->fail(YB_ERR_STATE, "yb_init_report needs an empty context");
     YB_CUDA(c, cudaSetDevice(c->device));
     std::vector<uint32_t> gp(1, 0);

@@ -57,6 +57,22 @@ class IdTable {
         off_.assign(1, 0);
         slots_.assign(1024, kNone);
     }
+    // Takes over an arena of distinct ids already in index order (parallel ingestion) and builds the lookup table.
+    void adopt(std::vector<char> &&bytes, std::vector<uint64_t> &&off) {
+        bytes_ = std::move(bytes);
+        off_ = std::move(off);
+        size_t cap = 1024;
+        while ((uint64_t)size() * 10 > (uint64_t)cap * 5) cap <<= 1;
+        slots_.assign(cap, kNone);
+        const size_t mask = cap - 1;
+        for (uint32_t i = 0; i < size(); ++i) {
+            size_t n;
+            const char *s = id(i, &n);
+            size_t p = (size_t)hash(s, n) & mask;
+            while (slots_[p] != kNone) p = (p + 1) & mask;
+            slots_[p] = i;
+        }
+    }
 
   private:
     static uint64_t hash(const char *s, size_t n) {
@@ -114,5 +130,19 @@ class Engine;  // capi.cu
 // add_overlap_and_length twice per record (src/reads2ovl/mod.rs:83-145). Returns false on error.
 typedef bool (*AddFn)(void *sink, const char *id, size_t id_len, uint32_t b, uint32_t e, uint64_t len);
 bool ingest_buffer(const char *text, size_t n, int format, AddFn add, void *sink, IngestError *err);
+
+// Multi-threaded form with the same observable result (first-seen read order, first-seen lengths, arrival order
+// inside a read), producing the CSR directly. `alloc` hands out the (pinned) rowptr[n_reads + 1], len[n_reads] and
+// iv[2 * n_iv] arrays once their sizes are known; the ids come back as one arena in read order.
+struct BulkIds {
+    std::vector<char> bytes;
+    std::vector<uint64_t> off;     // n_reads + 1
+    std::vector<uint64_t> length;  // first-seen length of every read (usize in the reference)
+    uint32_t n_reads = 0;
+    uint64_t n_iv = 0;
+};
+typedef bool (*CsrAllocFn)(void *sink, size_t n_reads, size_t n_iv, uint32_t **rowptr, uint32_t **len, uint32_t **iv);
+bool ingest_buffer_parallel(const char *text, size_t n, int format, int threads, CsrAllocFn alloc, void *sink, BulkIds *ids,
+                            IngestError *err);
 
 }  // namespace yb

@@ -181,4 +181,48 @@ int yb_synth_fill(const yb_synth_spec *sp, const uint32_t *global_idx, const uin
     return YB_OK;
 }
 
+// Synthetic PAF text for the ingestion bench: n_records overlap records between pseudo-random pairs of
+// n_reads reads ("read_0000123", per-read length fixed by the read index), 12 columns like minimap2's.
+// Returns the bytes needed; writes only when cap is large enough.
+uint64_t yb_synth_paf(uint64_t seed, uint32_t n_reads, uint64_t n_records, char *out, uint64_t cap) {
+    const uint64_t need = n_records * 96ull + 16;
+    if (!out || cap < need || n_reads == 0) return need;
+    char *p = out;
+    auto put = [&](uint64_t v) {
+        char tmp[24];
+        int n = 0;
+        do {
+            tmp[n++] = (char)('0' + v % 10);
+            v /= 10;
+        } while (v);
+        while (n) *p++ = tmp[--n];
+    };
+    auto put_id = [&](uint32_t r) {
+        memcpy(p, "read_", 5);
+        p += 5;
+        char tmp[8];
+        for (int i = 6; i >= 0; --i) {
+            tmp[i] = (char)('0' + r % 10);
+            r /= 10;
+        }
+        memcpy(p, tmp, 7);
+        p += 7;
+    };
+    for (uint64_t i = 0; i < n_records; ++i) {
+        Rng g(seed, i, 77);
+        const uint32_t a = (uint32_t)(g.next() % n_reads), b = (uint32_t)(g.next() % n_reads);
+        const uint32_t la = 500 + (uint32_t)(mix64(seed ^ (a * 0x9E3779B97F4A7C15ull)) % 60000);
+        const uint32_t lb = 500 + (uint32_t)(mix64(seed ^ (b * 0x9E3779B97F4A7C15ull)) % 60000);
+        const uint32_t ba = (uint32_t)(g.next() % (la - 1)), ea = ba + 1 + (uint32_t)(g.next() % (la - ba));
+        const uint32_t bb = (uint32_t)(g.next() % (lb - 1)), eb = bb + 1 + (uint32_t)(g.next() % (lb - bb));
+        put_id(a); *p++ = '\t'; put(la); *p++ = '\t'; put(ba); *p++ = '\t'; put(ea); *p++ = '\t';
+        *p++ = (i & 1) ? '-' : '+'; *p++ = '\t';
+        put_id(b); *p++ = '\t'; put(lb); *p++ = '\t'; put(bb); *p++ = '\t'; put(eb); *p++ = '\t';
+        put(ea - ba); *p++ = '\t'; put(ea - ba); *p++ = '\t';
+        memcpy(p, "255\n", 4);
+        p += 4;
+    }
+    return (uint64_t)(p - out);
+}
+
 }  // extern "C"
