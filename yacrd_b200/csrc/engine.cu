@@ -6,6 +6,10 @@
 // CUDA device yb_create fails.
 #include <cuda_runtime.h>
 #include <errno.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -596,12 +600,38 @@ int yb_init_file(yb_ctx *c, const char *path) {
     if (t != 'p' && t != 'm')
         return c->fail(YB_ERR_WRONG_FORMAT, "Can't run overlap parsing on %s file %s",
                        t == 'y' ? "yacrd" : (t == 'q' ? "fastq" : "fasta"), path);
+    // regular files are parsed in place from a read-only mapping; pipes and the like are read into memory
+    const char *data = nullptr;
+    size_t size = 0;
+    void *map = nullptr;
     std::vector<char> text;
-    if (int rc = slurp(c, path, &text)) return rc;
-    if (text.size() >= 2 && (unsigned char)text[0] == 0x1f && (unsigned char)text[1] == 0x8b)
-        return c->fail(YB_ERR_CANT_READ_FILE, "%s is gzip-compressed; decompress it first (compressed input is out of scope)", path);
-    const int rc = yb_init_buffer(c, text.data(), text.size(), t);
-    if (rc != YB_OK) c->error += std::string(" (Filename: ") + path + ")";
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return c->fail(YB_ERR_CANT_READ_FILE, "Can't open file %s: %s", path, strerror(errno));
+    struct stat sb;
+    if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+        map = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (map != MAP_FAILED) {
+            madvise(map, (size_t)sb.st_size, MADV_SEQUENTIAL | MADV_WILLNEED);
+            data = static_cast<const char *>(map);
+            size = (size_t)sb.st_size;
+        } else {
+            map = nullptr;
+        }
+    }
+    close(fd);
+    if (!map) {
+        if (int rc = slurp(c, path, &text)) return rc;
+        data = text.data();
+        size = text.size();
+    }
+    int rc;
+    if (size >= 2 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b)
+        rc = c->fail(YB_ERR_CANT_READ_FILE, "%s is gzip-compressed; decompress it first (compressed input is out of scope)", path);
+    else {
+        rc = yb_init_buffer(c, data, size, t);
+        if (rc != YB_OK) c->error += std::string(" (Filename: ") + path + ")";
+    }
+    if (map) munmap(map, size);
     return rc;
 }
 
