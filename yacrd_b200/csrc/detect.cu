@@ -23,8 +23,8 @@
 // Kernels (all integer work; no tensor cores — there is no contraction on this path):
 //   scatter_kernel   every row -> its size class (G = 1,2,3,4,5,6,8,10,16,32 lanes x 16 keys; packed or wide) and
 //                    a 16-byte worklist record {row, first interval, k, len}; rows with k > 512 -> big list.
-//   big_kernel       rows with k > 512: one CTA per row, 2k event keys bitonic-sorted in shared memory (or in
-//                    a global slab beyond 16384 events).
+//   big_kernel       rows with k > 512: one CTA per row; 512-key chunks sorted by warps in registers, larger strides
+//                    in shared memory (packed keys again; a global slab beyond 32768 intervals).
 //   sort_kernel      persistent warps walk the worklist in batches of floor(32 / G) rows of ONE class, so a
 //                    batch fills the warp with equal-sized lane groups. Each row's interval slab is pulled into
 //                    shared memory by its own TMA bulk copy (cp.async.bulk, SASS UBLKCP; double-buffered: the
@@ -69,12 +69,6 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
     return v;
 }
 
-__host__ __device__ inline uint64_t next_pow2_u64(uint64_t v) {
-    uint64_t p = 1;
-    while (p < v) p <<= 1;
-    return p;
-}
-
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // ------------------------------------------------------------------------------------------------
@@ -91,8 +85,6 @@ constexpr uint32_t kSortThreads = kSortWarps * 32;
 #define YB_SORT_MIN_CTAS (20 / YB_SORT_WARPS)
 #endif
 constexpr uint32_t kBufIntervals = 576;        // max over classes of floor(32/G) * (16 G + 2) row slots
-constexpr uint32_t kBigThreads = 512;
-constexpr uint32_t kBigSmemEvents = 16384;     // big_kernel: 64 KB of u32 event keys in shared memory
 constexpr uint32_t kScatterRows = 1024;        // rows per CTA of scatter_kernel
 constexpr uint32_t kPartShift = 8, kPartRows = 1u << kPartShift;  // rows per CTA of order_kernel
 constexpr uint32_t kStageChunk = 1024;       // pairs a warp reserves in the staging buffer per atomic
@@ -154,178 +146,6 @@ __global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Wor
     __syncthreads();
     if (cls >= 0)
         w.recs[tab.entry_base[cls] + s_base[cls] + wbase + rank] = make_uint4(r, p0, k | ((uint32_t)cls << 16) | kRecValid, len);
-}
-
-// ------------------------------------------------------------------------------------------------
-// big_kernel: one CTA per big row, event formulation (2k keys: begin 2b+1, end 2e; ends sort first at
-// equal positions, stack.rs:72-81), bitonic network in shared memory or in a global slab.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void check_interval(const uint2 v, uint32_t len, uint32_t *counters) {
-    if (!(v.x < v.y && v.y <= len)) atomicAdd(counters + kCntMalformed, 1u);
-}
-
-__device__ void cta_pileup(uint32_t *ev, uint32_t n_pow2, const uint2 *__restrict__ row, uint32_t k, uint32_t len,
-                           uint32_t c, double not_cov, uint32_t *__restrict__ flat, uint8_t *__restrict__ cls_out,
-                           uint32_t *__restrict__ cnt_out, uint32_t *sh /* 5 * 32 u32 */, uint32_t *counters) {
-    const uint32_t tid = threadIdx.x, nthr = blockDim.x, n_ev = 2u * k;
-    const uint32_t lane = lane_id(), wid = tid >> 5, nwarps = nthr >> 5;
-    for (uint32_t i = tid; i < n_pow2; i += nthr) {
-        uint32_t kk = INF;
-        if (i < n_ev) {
-            const uint2 v = __ldg(row + (i >> 1));
-            if (i & 1u) check_interval(v, len, counters);
-            kk = (i & 1u) ? v.y * 2u : v.x * 2u + 1u;
-        }
-        ev[i] = kk;
-    }
-    __syncthreads();
-    // all-ascending bitonic network over ev[0..n_pow2)
-    const uint32_t half_n = n_pow2 >> 1;
-    for (uint32_t size = 2; size <= n_pow2; size <<= 1) {
-        const uint32_t half = size >> 1;
-        for (uint32_t p = tid; p < half_n; p += nthr) {
-            const uint32_t blk = p / half, o = p - blk * half;
-            const uint32_t lo = blk * size + o, hi = blk * size + size - 1u - o;
-            const uint32_t x = ev[lo], y = ev[hi];
-            if (x > y) {
-                ev[lo] = y;
-                ev[hi] = x;
-            }
-        }
-        __syncthreads();
-        for (uint32_t stride = size >> 2; stride > 0; stride >>= 1) {
-            for (uint32_t p = tid; p < half_n; p += nthr) {
-                const uint32_t lo = 2u * stride * (p / stride) + (p % stride), hi = lo + stride;
-                const uint32_t x = ev[lo], y = ev[hi];
-                if (x > y) {
-                    ev[lo] = y;
-                    ev[hi] = x;
-                }
-            }
-            __syncthreads();
-        }
-    }
-    // Each warp owns a contiguous chunk of the sorted events and walks it 32 events per round;
-    // depth inside a round comes from two ballots (begins, ends) and popc.
-    uint32_t *sh_delta = sh, *sh_cross = sh + 32, *sh_first = sh + 64, *sh_last = sh + 96, *sh_bad = sh + 128;
-    uint32_t chunk = n_pow2 / nwarps;
-    if (chunk < 32u) chunk = 32u;
-    const uint32_t beg = min(wid * chunk, n_ev), end = min(beg + chunk, n_ev);
-    const uint32_t le = (2u << lane) - 1u, lt = (1u << lane) - 1u;
-    uint32_t dsum = 0;
-    for (uint32_t i0 = beg; i0 < end; i0 += 32u) {
-        const uint32_t i = i0 + lane;
-        const bool real = i < end;
-        const uint32_t kb = real ? (ev[i] & 1u) : 0u;
-        const uint32_t bm = __ballot_sync(FULL, real && kb), em = __ballot_sync(FULL, real && !kb);
-        dsum += __popc(bm) - __popc(em);
-    }
-    if (lane == 0) sh_delta[wid] = dsum;
-    __syncthreads();
-    uint32_t depth0 = 0;
-    for (uint32_t q = 0; q < wid; ++q) depth0 += sh_delta[q];
-    const uint32_t cu = c + 1u;
-    uint32_t d0 = depth0, ncross = 0, badsum = 0, firstpos = 0, lastpos = 0;
-    for (uint32_t i0 = beg; i0 < end; i0 += 32u) {
-        const uint32_t i = i0 + lane;
-        const bool real = i < end;
-        const uint32_t kk = real ? ev[i] : 0u;
-        const uint32_t kb = real ? (kk & 1u) : 0u, pos = kk >> 1;
-        const uint32_t bm = __ballot_sync(FULL, real && kb), em = __ballot_sync(FULL, real && !kb);
-        const uint32_t depth = d0 + __popc(bm & le) - __popc(em & le);
-        const bool up = real && kb && depth == cu, down = real && !kb && depth == c;
-        const uint32_t xm = __ballot_sync(FULL, up || down);
-        if (xm) {
-            const uint32_t f = __shfl_sync(FULL, pos, __ffs(xm) - 1);
-            const uint32_t l = __shfl_sync(FULL, pos, 31 - __clz(xm));
-            if (ncross == 0) firstpos = f;
-            lastpos = l;
-            ncross += __popc(xm);
-        }
-        badsum += up ? pos : (down ? 0u - pos : 0u);
-        d0 += __popc(bm) - __popc(em);
-    }
-    badsum = warp_sum(badsum);
-    if (lane == 0) {
-        sh_cross[wid] = ncross;
-        sh_first[wid] = firstpos;
-        sh_last[wid] = lastpos;
-        sh_bad[wid] = badsum;
-    }
-    __syncthreads();
-    uint32_t X = 0, xbase = 0, U0 = 0, Dl = 0, bad = 0;
-    for (uint32_t q = 0; q < nwarps; ++q) {
-        const uint32_t n = sh_cross[q];
-        if (q == wid) xbase = X;
-        if (n) {
-            if (X == 0) U0 = sh_first[q];
-            Dl = sh_last[q];
-        }
-        X += n;
-        bad += sh_bad[q];
-    }
-    uint32_t n_gaps, h = 0;
-    if (X) {
-        h = U0 != 0u;
-        n_gaps = (X >> 1) - 1u + h + (Dl != len ? 1u : 0u);
-        uint32_t x = xbase;
-        d0 = depth0;
-        // crossing number x lands at flat[x + 2h - 1]
-        for (uint32_t i0 = beg; i0 < end; i0 += 32u) {
-            const uint32_t i = i0 + lane;
-            const bool real = i < end;
-            const uint32_t kk = real ? ev[i] : 0u;
-            const uint32_t kb = real ? (kk & 1u) : 0u, pos = kk >> 1;
-            const uint32_t bm = __ballot_sync(FULL, real && kb), em = __ballot_sync(FULL, real && !kb);
-            const uint32_t depth = d0 + __popc(bm & le) - __popc(em & le);
-            const bool cross = real && ((kb && depth == cu) || (!kb && depth == c));
-            const uint32_t xm = __ballot_sync(FULL, cross);
-            if (cross) {
-                const int idx = (int)(x + __popc(xm & lt) + 2u * h) - 1;
-                if (idx >= 0) flat[idx] = pos;
-            }
-            x += __popc(xm);
-            d0 += __popc(bm) - __popc(em);
-        }
-        if (tid == 0) {
-            if (h) flat[0] = 0u;
-            if (Dl != len) flat[X + 2u * h - 1u] = len;
-        }
-    } else {
-        n_gaps = len != 0u;
-        if (tid == 0 && n_gaps) {
-            flat[0] = 0u;
-            flat[1] = len;
-        }
-    }
-    if (tid == 0) {
-        *cls_out = (uint8_t)classify(len + bad, len, X >> 1, not_cov);
-        *cnt_out = n_gaps;
-    }
-}
-
-__global__ void __launch_bounds__(kBigThreads) big_kernel(DetectArgs a, Work w, uint32_t c, double not_cov) {
-    extern __shared__ uint32_t ev_smem[];
-    __shared__ uint32_t sh[160];
-    __shared__ uint32_t sh_off, sh_stage;
-    const uint32_t n_big = a.counters[kCntBigList];
-    for (uint32_t j = blockIdx.x; j < n_big; j += gridDim.x) {
-        const uint32_t r = w.big_list[j];
-        const uint32_t s = a.rowptr[r], k = a.rowptr[r + 1] - s;
-        const uint32_t n_pow2 = (uint32_t)next_pow2_u64(2ull * k);
-        uint32_t *ev = ev_smem;
-        if (threadIdx.x == 0) {  // room for the row's k + 1 possible bad regions
-            sh_stage = atomicAdd(a.counters + kCntStage, k + 1u);
-            w.soff[r] = sh_stage;
-            if (n_pow2 > kBigSmemEvents) sh_off = atomicAdd(a.counters + kCntHugeBump, n_pow2);  // keys in a global slab
-        }
-        __syncthreads();
-        if (n_pow2 > kBigSmemEvents) ev = w.huge_keys + sh_off;
-        cta_pileup(ev, n_pow2, a.iv + s, k, a.len[r], c, not_cov, reinterpret_cast<uint32_t *>(w.stage + sh_stage),
-                   a.cls + r, a.gap_ptr + r, sh, a.counters);
-        if (threadIdx.x == 0 && a.gap_ptr[r]) atomicAdd(w.part_total + (r >> kPartShift), a.gap_ptr[r]);
-        __syncthreads();
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -395,6 +215,247 @@ template <bool PK> __device__ __forceinline__ void sort_group(uint32_t (&key)[E]
             for (int t = 0; t < E; ++t)
                 if ((t & s) == 0) ce<PK>(key[t], key[t | s]);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA tier (big_kernel): rows with k > 512, one CTA per row. The same closed form as the register tier on arrays
+// that live in shared memory (or, beyond kCtaMaxSmemWords, in a global slab): 512-key chunks are sorted by a warp in
+// registers (sort_group, G = 32), larger strides are compare-exchanged in place, and every level is finished by
+// warps merging 512-key blocks in registers again, so a level costs log2(size / 512) passes over the array
+// instead of log2(size). PK: one array of begin | end << 16; else two u32 arrays (begins, ends).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kCtaThreads = 256;
+constexpr uint32_t kCtaMaxSmemWords = 32768u + 2048u;  // 136 KB: k <= 32768 packed, k <= 16384 wide
+
+__host__ __device__ inline uint32_t cta_idx(uint32_t e) { return e + (e >> 4); }  // 17-word pitch per 16 keys
+__host__ __device__ inline uint64_t cta_words(uint64_t k, bool wide) {
+    uint64_t K = 512;
+    while (K < k) K <<= 1;
+    return (wide ? 2ull : 1ull) * (K + (K >> 4));
+}
+
+// bitonic merge of the 512 keys a warp holds (blocked, 16 per lane) once they form a bitonic sequence
+template <bool PK> __device__ __forceinline__ void merge512(uint32_t (&key)[E]) {
+    const uint32_t lane = lane_id();
+#pragma unroll 1
+    for (uint32_t j = 16; j > 0; j >>= 1) {
+        const bool lo_half = (lane & j) == 0;
+#pragma unroll
+        for (int t = 0; t < E; ++t) {
+            const uint32_t o = __shfl_xor_sync(FULL, key[t], j);
+            key[t] = lo_half ? kmin<PK>(key[t], o) : kmax<PK>(key[t], o);
+        }
+    }
+#pragma unroll
+    for (int s = E >> 1; s > 0; s >>= 1) {
+#pragma unroll
+        for (int t = 0; t < E; ++t)
+            if ((t & s) == 0) ce<PK>(key[t], key[t | s]);
+    }
+}
+
+template <bool PK> __device__ __forceinline__ void cta_ce(uint32_t *keys, uint32_t lo, uint32_t hi) {
+    const uint32_t x = keys[cta_idx(lo)], y = keys[cta_idx(hi)];
+    keys[cta_idx(lo)] = kmin<PK>(x, y);
+    keys[cta_idx(hi)] = kmax<PK>(x, y);
+}
+
+// Finishes the sort of `arrays` arrays of K keys whose 512-key chunks are already sorted (K a power of two >= 512);
+// array q sits at keys + q * (K + K / 16).
+template <bool PK> __device__ void cta_merge_levels(uint32_t *keys, uint32_t K, uint32_t arrays) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5, nwarps = kCtaThreads / 32;
+    const uint32_t pitch = K + (K >> 4);
+    for (uint32_t size = 1024, lg = 10; size <= K; size <<= 1, ++lg) {
+        for (uint32_t q = 0; q < arrays; ++q) {
+            uint32_t *a = keys + q * pitch;
+            for (uint32_t p = tid; p < (K >> 1); p += kCtaThreads) {  // flip: e <-> e ^ (size - 1)
+                const uint32_t blk = p >> (lg - 1), o = p & ((size >> 1) - 1u);
+                cta_ce<PK>(a, (blk << lg) + o, (blk << lg) + size - 1u - o);
+            }
+        }
+        __syncthreads();
+        for (uint32_t stride = size >> 2, ls = lg - 2; stride >= 512u; stride >>= 1, --ls) {
+            for (uint32_t q = 0; q < arrays; ++q) {
+                uint32_t *a = keys + q * pitch;
+                for (uint32_t p = tid; p < (K >> 1); p += kCtaThreads) {
+                    const uint32_t lo = ((p >> ls) << (ls + 1)) | (p & (stride - 1u));
+                    cta_ce<PK>(a, lo, lo + stride);
+                }
+            }
+            __syncthreads();
+        }
+        for (uint32_t q = 0; q < arrays; ++q) {  // strides 256 .. 1: 512-key blocks, in registers
+            uint32_t *a = keys + q * pitch;
+            for (uint32_t blk = wid; blk < (K >> 9); blk += nwarps) {
+                uint32_t *b = a + cta_idx(blk * 512u) + 17u * lane;
+                uint32_t key[E];
+#pragma unroll
+                for (int t = 0; t < E; ++t) key[t] = b[t];
+                merge512<PK>(key);
+#pragma unroll
+                for (int t = 0; t < E; ++t) b[t] = key[t];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Block-wide exclusive scan of one value per thread (kCtaThreads threads); *total gets the sum. sh: 8 words.
+__device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t *sh, uint32_t *total) {
+    const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
+    const uint32_t incl = warp_incl_scan(v);
+    __syncthreads();
+    if (lane == 31u) sh[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < kCtaThreads / 32; ++q) {
+        const uint32_t x = sh[q];
+        before += q < wid ? x : 0u;
+        tot += x;
+    }
+    *total = tot;
+    return before + incl - v;
+}
+
+template <bool PK>
+__device__ void cta_row(const DetectArgs &a, const Work &w, uint32_t *keys, uint32_t r, uint32_t c, uint32_t *sh /* 16 u32 */) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5, nwarps = kCtaThreads / 32;
+    const uint32_t s = a.rowptr[r], k = a.rowptr[r + 1] - s, len = a.len[r];
+    const uint2 *row = a.iv + s;
+    uint32_t K = 512;
+    while (K < k) K <<= 1;
+    const uint32_t pitch = K + (K >> 4);
+    uint32_t *kB = keys, *kE = keys + (PK ? 0u : pitch);
+    // ---- 512-key chunks: load, validate, sort in registers, store blocked ----
+    bool bad_iv = false;
+    for (uint32_t ch = wid; ch < (K >> 9); ch += nwarps) {
+        uint32_t K0[E], K1[PK ? 1 : E];
+#pragma unroll
+        for (int t = 0; t < E; ++t) {
+            const uint32_t e = ch * 512u + (uint32_t)t * 32u + lane;
+            uint2 v = make_uint2(INF, INF);
+            if (e < k) {
+                v = __ldg(row + e);
+                bad_iv |= !(v.x < v.y && v.y <= len);
+            }
+            if (PK) {
+                K0[t] = __byte_perm(v.x, v.y, 0x5410);
+            } else {
+                K0[t] = v.x;
+                K1[PK ? 0 : t] = v.y;
+            }
+        }
+        sort_group<PK>(K0, 32u, lane, true);
+        uint32_t *b = kB + cta_idx(ch * 512u) + 17u * lane;
+#pragma unroll
+        for (int t = 0; t < E; ++t) b[t] = K0[t];
+        if (!PK) {
+            uint32_t Kx[E];
+#pragma unroll
+            for (int t = 0; t < E; ++t) Kx[t] = K1[PK ? 0 : t];
+            sort_group<PK>(Kx, 32u, lane, true);
+            uint32_t *eb = kE + cta_idx(ch * 512u) + 17u * lane;
+#pragma unroll
+            for (int t = 0; t < E; ++t) eb[t] = Kx[t];
+        }
+    }
+    if (__any_sync(FULL, bad_iv) && lane == 0) atomicAdd(a.counters + kCntMalformed, 1u);
+    __syncthreads();
+    cta_merge_levels<PK>(keys, K, PK ? 1u : 2u);
+    // ---- crossings: thread t owns the contiguous slots [i0, i1) ----
+    const uint32_t BINF = PK ? 0xFFFFu : INF;
+    const uint32_t cc = min(c, K);  // beyond k every threshold behaves the same
+    auto Bv = [&](uint32_t i) -> uint32_t { return i >= K ? BINF : (PK ? (kB[cta_idx(i)] & 0xFFFFu) : kB[cta_idx(i)]); };
+    auto Ev = [&](uint32_t i, uint32_t back) -> uint32_t {  // E[i - back], 0 below the first end
+        if (i < back) return 0u;
+        const uint32_t j = i - back;
+        return PK ? (kE[cta_idx(j)] >> 16) : kE[cta_idx(j)];
+    };
+    const uint32_t per = K / kCtaThreads, i0 = tid * per, i1 = i0 + per;
+    uint32_t nu = 0, nd = 0, firstU = 0, lastD = 0;
+    for (uint32_t i = i0; i < i1; ++i) {
+        const uint32_t bi = Bv(i), bn = Bv(i + 1u), e1 = Ev(i, cc + 1u), e0 = Ev(i, cc);
+        const bool v1 = e1 <= bi, v0 = e0 <= bi, v1n = e0 <= bn;
+        if (v1 && !v0) {
+            if (nu == 0) firstU = bi;
+            ++nu;
+        }
+        if (!v0 && v1n) {
+            lastD = e0;
+            ++nd;
+        }
+    }
+    uint32_t n_up, n_down;
+    const uint32_t ru0 = cta_excl_scan(nu, sh, &n_up);
+    const uint32_t rd0 = cta_excl_scan(nd, sh, &n_down);
+    __syncthreads();
+    if (nu && ru0 == 0u) sh[8] = firstU;
+    if (nd && rd0 + nd == n_down) sh[9] = lastD;
+    if (tid == 0) sh[10] = atomicAdd(a.counters + kCntStage, k + 1u);  // room for the row's k + 1 possible bad regions
+    __syncthreads();
+    const uint32_t U0 = sh[8], Dl = sh[9], at = sh[10];
+    uint32_t ng, h = 0, tail = 0;
+    if (n_up) {
+        h = U0 != 0u;
+        tail = Dl != len;
+        ng = n_up - 1u + h + tail;
+    } else {
+        ng = h = tail = len != 0u;
+    }
+    const bool fits = (uint64_t)at + k + 1u <= w.stage_cap;
+    if (!fits) ng = 0;
+    uint32_t *F = reinterpret_cast<uint32_t *>(w.stage + at);
+    if (fits && n_up) {
+        // flat layout [0 if h] U0 D0 U1 D1 ... [len if tail]: U_j sits at 2j - 1 + 2h, D_j at 2j + 2h
+        uint32_t ru = ru0, rd = rd0;
+        for (uint32_t i = i0; i < i1; ++i) {
+            const uint32_t bi = Bv(i), bn = Bv(i + 1u), e1 = Ev(i, cc + 1u), e0 = Ev(i, cc);
+            const bool v1 = e1 <= bi, v0 = e0 <= bi, v1n = e0 <= bn;
+            if (v1 && !v0) {
+                const int f = 2 * (int)ru - 1 + 2 * (int)h;
+                if (f >= 0) F[f] = bi;
+                ++ru;
+            }
+            if (!v0 && v1n) {
+                const uint32_t f = 2u * rd + 2u * h;
+                if (f < 2u * ng) F[f] = e0;
+                ++rd;
+            }
+        }
+    }
+    if (tid == 0) {
+        if (fits) {
+            if (h) F[0] = 0u;
+            if (tail) F[2u * ng - 1u] = len;
+        } else {
+            atomicAdd(a.counters + kCntStageOverflow, 1u);
+        }
+        a.gap_ptr[r] = ng;  // count for now; order_kernel turns it into the offset
+        w.soff[r] = at;
+        if (ng) atomicAdd(w.part_total + (r >> kPartShift), ng);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kCtaThreads) big_kernel(DetectArgs a, Work w, uint32_t c, uint32_t smem_words) {
+    extern __shared__ __align__(16) uint32_t cta_smem[];
+    __shared__ uint32_t sh[16];
+    const uint32_t n_big = a.counters[kCntBigList];
+    for (uint32_t j = blockIdx.x; j < n_big; j += gridDim.x) {
+        const uint32_t r = w.big_list[j];
+        const uint32_t k = a.rowptr[r + 1] - a.rowptr[r];
+        const bool wide = a.len[r] > kPackedMaxLen;
+        const uint64_t words = cta_words(k, wide);
+        uint32_t *keys = cta_smem;
+        if (words > smem_words) {  // keys live in a bump-allocated global slab
+            if (threadIdx.x == 0) sh[11] = atomicAdd(a.counters + kCntHugeBump, (uint32_t)words);
+            __syncthreads();
+            keys = w.huge_keys + sh[11];
+        }
+        if (wide) cta_row<false>(a, w, keys, r, c, sh);
+        else cta_row<true>(a, w, keys, r, c, sh);
     }
 }
 
@@ -862,8 +923,8 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
             if (cls < 0) {  // big row: rare, straight to the global sums
                 cls = kNumClasses;
                 atomicAdd(&out->big_pairs, (unsigned long long)k + 1ull);
-                const unsigned long long hk = next_pow2_u64(2ull * k);
-                if (hk > kBigSmemEvents) atomicAdd(&out->huge_keys, hk);
+                const unsigned long long hk = cta_words(k, l > kPackedMaxLen);
+                if (hk > kCtaMaxSmemWords) atomicAdd(&out->huge_keys, hk);
             }
             if (l > kPackedMaxLen) atomicAdd(&s_bad[2], 1u);
         }
@@ -922,8 +983,8 @@ int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_rea
 }
 
 uint64_t huge_keys_for_row(uint64_t k) {
-    const uint64_t p = next_pow2_u64(2 * k);
-    return (k > kSmallMaxK && p > kBigSmemEvents) ? p : 0;
+    const uint64_t p = cta_words(k, true);
+    return (k > kSmallMaxK && p > kCtaMaxSmemWords) ? p : 0;
 }
 uint64_t big_pairs_for_row(uint64_t k) { return k > kSmallMaxK ? k + 1 : 0; }
 
@@ -942,7 +1003,7 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         int dev = 0, sm = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return -1;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBigSmemEvents * sizeof(uint32_t))) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCtaMaxSmemWords * sizeof(uint32_t))) != cudaSuccess) return -1;
         if (cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return -1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, sort_kernel, kSortThreads, kSortSmemBytes) != cudaSuccess) return -1;
         if (occ_sort < 1) return -1;
@@ -985,9 +1046,15 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, tab);
     ++launches;
     if (a.rows.n_big) {
-        uint32_t grid = (uint32_t)n_sm * 2u;
+        // shared memory for the largest row (wide if any read is); rows beyond kCtaMaxSmemWords sort in a global slab
+        uint64_t words = cta_words(a.max_k, a.rows.n_wide != 0);
+        if (words > kCtaMaxSmemWords) words = kCtaMaxSmemWords;
+        uint32_t per_sm = (uint32_t)((220u * 1024u) / (words * 4u + 1024u));
+        if (per_sm < 1u) per_sm = 1u;
+        if (per_sm > 8u) per_sm = 8u;
+        uint32_t grid = (uint32_t)n_sm * per_sm;
         if (grid > a.rows.n_big) grid = (uint32_t)a.rows.n_big;
-        big_kernel<<<grid, kBigThreads, kBigSmemEvents * sizeof(uint32_t), stream>>>(a, w, coverage, not_coverage);
+        big_kernel<<<grid, kCtaThreads, words * sizeof(uint32_t), stream>>>(a, w, coverage, (uint32_t)words);
         ++launches;
     }
     if (items) {
