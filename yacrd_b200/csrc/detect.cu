@@ -536,23 +536,39 @@ __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w
     // striped load (conflict-free); the initial arrangement is irrelevant to the sort
     uint32_t K0[E];             // PK: begin | end << 16; else begins
     uint32_t K1[PK ? 1 : E];    // else ends
+    // validity 0 <= b < e <= len: one compare per interval for b < e, a running maximum of the ends for e <= len
     bool bad_iv = false;
+    uint32_t emax = 0;
+    const uint2 *lane_iv = slot + g;           // this lane's elements: g, g + G, g + 2G, ...
+    const uint32_t left = k > g ? k - g : 0u;  // element t exists iff t * G < left
+    auto load16 = [&](const uint32_t GG) {     // GG: the batch's G as a compile-time constant where it is a common one
 #pragma unroll
-    for (int t = 0; t < E; ++t) {
-        const uint32_t e = (uint32_t)t * G + g;
-        uint2 v = make_uint2(INF, INF);
-        if (e < k) {
-            v = slot[e];
-            bad_iv |= !(v.x < v.y && v.y <= len);
+        for (int t = 0; t < E; ++t) {
+            uint2 v = make_uint2(INF, INF);
+            if ((uint32_t)t * GG < left) {
+                v = lane_iv[(uint32_t)t * GG];
+                bad_iv |= v.x >= v.y;
+                emax = max(emax, v.y);
+            }
+            if (PK) {
+                K0[t] = __byte_perm(v.x, v.y, 0x5410);
+            } else {
+                K0[t] = v.x;
+                K1[PK ? 0 : t] = v.y;
+            }
         }
-        if (PK) {
-            K0[t] = __byte_perm(v.x, v.y, 0x5410);
-        } else {
-            K0[t] = v.x;
-            K1[PK ? 0 : t] = v.y;
-        }
+    };
+    switch (G) {  // constant strides turn the address arithmetic into immediates
+        case 1: load16(1); break;
+        case 2: load16(2); break;
+        case 3: load16(3); break;
+        case 4: load16(4); break;
+        case 5: load16(5); break;
+        case 6: load16(6); break;
+        case 8: load16(8); break;
+        default: load16(G); break;
     }
-    malformed += bad_iv;
+    malformed += (bad_iv || emax > len) ? 1u : 0u;
     if (PK) {
         sort_group<PK>(K0, G, g, geo.in_group);
     } else {
@@ -739,12 +755,12 @@ __global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(De
     uint32_t q = 0, malformed = 0;
     // Dynamic schedule (batches cost between 0.3 and 2 us): a warp draws batch indices from one counter, three
     // batches ahead, so the atomic's latency hides behind a whole batch. Indices drawn by a warp only grow.
-    auto draw = [&]() {
+    auto draw_raw = [&]() {  // lane 0 holds the index; nobody waits for the atomic until the value is broadcast
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(a.counters + kCntTile, 1u);
-        return __shfl_sync(FULL, t, 0);
+        return t;
     };
-    uint32_t item = draw(), item1 = draw(), item2 = draw();
+    uint32_t item = __shfl_sync(FULL, draw_raw(), 0), item1 = __shfl_sync(FULL, draw_raw(), 0), item2 = __shfl_sync(FULL, draw_raw(), 0);
     // software pipeline: records of batch i+2 are loaded, the slabs of batch i+1 are in flight, batch i is sorted
     uint32_t cls0, cls1, cls2;
     uint4 rec0 = load_rec(w, tab, item, n_items, q, cls0);
@@ -754,7 +770,7 @@ __global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(De
     uint32_t b = 0, parity = 0;
     uint2 chunk = make_uint2(0, 0);  // [next free pair, end) of the warp's staging chunk
     while (item < n_items) {
-        const uint32_t item3 = draw();
+        const uint32_t raw3 = draw_raw();  // consumed at the end of this iteration
         const uint4 rec2 = load_rec(w, tab, item2, n_items, q, cls2);
         uint2 *buf = buf0 + b * kBufIntervals;
         mbar_wait(&ws.mbar[b], parity);
@@ -771,7 +787,7 @@ __global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(De
         cls1 = cls2;
         item = item1;
         item1 = item2;
-        item2 = item3;
+        item2 = __shfl_sync(FULL, raw3, 0);
         parity ^= b;
         b ^= 1u;
     }
