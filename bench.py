@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 10)")
     ap.add_argument("--ref-sample", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-allgather", action="store_true", help="N > 1: NCCL all-gather instead of the peer-memory epilogue")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph per step")
     args = ap.parse_args()
 
@@ -173,8 +174,22 @@ def main():
     fm.synchronize()
     _, _, counts = ybd.shard_layout(n_glob, world)
     slot = ybd.bitmap_bytes(int(counts.max()))
-    gathered = torch.zeros(world, slot, dtype=torch.uint8, device=dev)
-    fm.bind_device_bitmap(gathered[rank].data_ptr(), slot)
+    # N > 1: the all-gather of the bitmap is fused into the kernels' epilogue over NVLink peer memory (CUDA IPC
+    # buffers, yacrd_b200/dist.py:PeerGather); --nccl-allgather times the plain NCCL collective instead
+    pg = None
+    if use_dist and not args.nccl_allgather:
+        try:
+            pg = ybd.PeerGather(fm, slot)
+        except Exception as e:
+            sys.stderr.write("peer-memory all-gather unavailable (%r): using NCCL\n" % (e,))
+        ok = torch.tensor([1 if pg is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if pg is not None and int(ok.item()) == 0:
+            pg.close()
+            pg = None
+    gathered = pg.tensor() if pg is not None else torch.zeros(world, slot, dtype=torch.uint8, device=dev)
+    if pg is None:
+        fm.bind_device_bitmap(gathered[rank].data_ptr(), slot)
     # a non-default stream: the C ABI takes NULL as "the context's own stream", and CUDA events only see
     # the stream they are recorded on, so kernels, all-gather and events all go to this one
     stream = torch.cuda.Stream(device=dev)
@@ -186,7 +201,7 @@ def main():
 
     def step():
         fm.compute_device(c, nn, stream.cuda_stream)
-        if use_dist:
+        if use_dist and pg is None:
             ybd.allgather_bitmaps(gathered[rank], gathered)
 
     def barrier():
@@ -223,7 +238,7 @@ def main():
     def run_step():
         if graph is not None:
             graph.replay()
-            if use_dist:
+            if use_dist and pg is None:
                 ybd.allgather_bitmaps(gathered[rank], gathered)
         else:
             step()
@@ -277,17 +292,20 @@ def main():
     # ---- end-to-end arm: public API, pinned host CSR in, host results out, every step ------------
     fm2 = yb.FullMemory(device=local_rank)
     ke = args.e2e_steps or min(K, 10)
-    gathered2 = torch.zeros(world, slot, dtype=torch.uint8, device=dev)
+    pg2 = ybd.PeerGather(fm2, slot) if pg is not None else None
+    gathered2 = pg2.tensor() if pg2 is not None else torch.zeros(world, slot, dtype=torch.uint8, device=dev)
     host_gathered = torch.empty(world, slot, dtype=torch.uint8).pin_memory()
 
     def e2e_step():
         fm2.reset()
         fm2.bind_csr(csr)                              # host buffers (pinned)
-        fm2.bind_device_bitmap(gathered2[rank].data_ptr(), slot)
+        if pg2 is None:
+            fm2.bind_device_bitmap(gathered2[rank].data_ptr(), slot)
         bp = yb.FromOverlap(fm2, c, nn)
         bp.compute_all_bad_part()                      # H2D + kernels + D2H of classes / bad-region CSR
         if use_dist:
-            ybd.allgather_bitmaps(gathered2[rank], gathered2)
+            if pg2 is None:
+                ybd.allgather_bitmaps(gathered2[rank], gathered2)
             host_gathered.copy_(gathered2, non_blocking=False)
         return int(bp.classes()[:16].sum()) + len(bp.gap_csr()[1])
 
@@ -337,8 +355,9 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": desc, "seed": SEED, "reads_global": n_glob, "reads_rank0": csr.n_reads,
-                       "intervals_rank0": csr.n_iv, "sharding": "mix64(read index) % n_gpus, no data-path collective; "
-                       "one all-gather of the 2-bit class bitmap per step" if use_dist else "single GPU",
+                       "intervals_rank0": csr.n_iv, "sharding": ("mix64(read index) % n_gpus, no data-path collective; the 2-bit class bitmap is all-gathered every step "
+                                    + ("by peer stores from the kernels' epilogue + flag barrier (NVLink, CUDA IPC)" if pg is not None
+                                       else "with one NCCL all-gather")) if use_dist else "single GPU",
                        "l2": "inputs larger than L2 (%.0f MB per rank)" % (in_bytes / 1e6) if flush is None
                        else "L2 flushed (256 MB memset) before every timed step; steps timed individually",
                        "classes_rank0": dict(zip(["NotBad", "Chimeric", "NotCovered"], class_counts)),
@@ -353,6 +372,12 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }), flush=True)
+    if use_dist:
+        torch.cuda.synchronize()
+        dist.barrier()
+    for g_ in (pg, pg2):
+        if g_ is not None:
+            g_.close()
     fm.close()
     fm2.close()
     if use_dist:

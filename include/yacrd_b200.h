@@ -170,6 +170,27 @@ void *yb_device_class_bitmap(yb_ctx *ctx, size_t *n_bytes);
  * slot of an in-place all-gather buffer); n_bytes >= 4*ceil(n_reads/16). NULL unbinds. */
 int yb_bind_device_bitmap(yb_ctx *ctx, void *device_ptr, size_t n_bytes);
 void *yb_stream(yb_ctx *ctx); /* the context's cudaStream_t */
+
+/* ---- peer-memory all-gather of the class bitmap (one process per GPU, same node, NVLink / NVSwitch) -------
+ * Instead of a separate collective after the kernels, the ordering kernel stores every word of this rank's 2-bit
+ * bitmap straight into slot `rank` of EVERY rank's gather buffer ([n_ranks x slot_bytes], peer stores over NVLink),
+ * and a one-CTA kernel closes the step with a flag barrier (release / acquire at system scope), so that when the
+ * stream reaches the end of yb_compute_device every rank holds every rank's bitmap. Buffers are plain cudaMalloc
+ * allocations shared through CUDA IPC handles, which the caller exchanges with whatever it has (torch.distributed,
+ * MPI, a file). */
+#define YB_IPC_HANDLE_BYTES 64
+#define YB_MAX_PEERS 16
+/* Device buffer (zero-filled) that other processes can map; handle_out receives YB_IPC_HANDLE_BYTES bytes. */
+void *yb_peer_alloc(yb_ctx *ctx, size_t n_bytes, void *handle_out);
+/* Maps a buffer another process allocated with yb_peer_alloc. */
+void *yb_peer_open(yb_ctx *ctx, const void *handle);
+int yb_peer_close(yb_ctx *ctx, void *mapped);
+int yb_peer_free(yb_ctx *ctx, void *allocated);
+/* gather_bufs[p] / flag_bufs[p]: rank p's gather buffer (n_ranks x slot_bytes bytes) and flag buffer (128 bytes,
+ * zero-filled), as mapped in THIS process (own buffers for p == rank). Every rank must run the same number of
+ * detect steps (the barrier counts them). n_ranks == 0 unbinds. */
+int yb_bind_peers(yb_ctx *ctx, void *const *gather_bufs, void *const *flag_bufs, uint32_t n_ranks, uint32_t rank,
+                  size_t slot_bytes);
 void *yb_device_classes(yb_ctx *ctx, size_t *n);
 void *yb_device_gap_ptr(yb_ctx *ctx, size_t *n);
 void *yb_device_gaps(yb_ctx *ctx, size_t *n_pairs_capacity);

@@ -92,6 +92,11 @@ SIGNATURES = {
     "yb_synth_shard_of": (C.c_uint32, [C.c_uint32, C.c_uint32]),
     "yb_synth_count": (C.c_uint32, [C.POINTER(YbSynthSpec)]),
     "yb_synth_plan": (C.c_uint64, [C.POINTER(YbSynthSpec), _vp, _vp, _vp]),
+    "yb_peer_alloc": (_vp, [_vp, _sz, _vp]),
+    "yb_peer_open": (_vp, [_vp, _vp]),
+    "yb_peer_close": (C.c_int, [_vp, _vp]),
+    "yb_peer_free": (C.c_int, [_vp, _vp]),
+    "yb_bind_peers": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _sz]),
     "yb_synth_paf": (C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint64, _vp, C.c_uint64]),
     "yb_synth_fill": (C.c_int, [C.POINTER(YbSynthSpec), _vp, _vp, _vp, C.c_uint32, _vp, C.c_int]),
 }

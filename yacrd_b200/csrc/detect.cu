@@ -873,7 +873,13 @@ __global__ void __launch_bounds__(kPartRows) order_kernel(DetectArgs a, Work w, 
     bits |= __shfl_xor_sync(FULL, bits, 2);
     bits |= __shfl_xor_sync(FULL, bits, 4);
     bits |= __shfl_xor_sync(FULL, bits, 8);
-    if ((lane & 15u) == 0u && live) reinterpret_cast<uint32_t *>(a.bitmap)[r >> 4] = bits;
+    if ((lane & 15u) == 0u && live) {
+        if (a.n_peers == 0u) {
+            reinterpret_cast<uint32_t *>(a.bitmap)[r >> 4] = bits;
+        } else {  // all-gather fused into the epilogue: the word goes to this rank's slot on every rank (NVLink stores)
+            for (uint32_t p = 0; p < a.n_peers; ++p) reinterpret_cast<uint32_t *>(a.peer_slot[p])[r >> 4] = bits;
+        }
+    }
     // class histogram: one RED per class per CTA, spread over kHistSlots copies (same-address atomics serialise in L2)
     const uint32_t h1 = __popc(__ballot_sync(FULL, cl == 1u)), h2 = __popc(__ballot_sync(FULL, cl == 2u));
     if (lane == 0) s_hist[wid] = h1 | (h2 << 16);
@@ -889,6 +895,32 @@ __global__ void __launch_bounds__(kPartRows) order_kernel(DetectArgs a, Work w, 
         if (c1) atomicAdd(slot + 1, c1);
         if (c2) atomicAdd(slot + 2, c2);
     }
+}
+
+// Closes a step of the peer-memory all-gather: thread p tells rank p "rank `rank` has written its slot for `epoch`"
+// and then waits until rank p has said the same here. Bounded wait: a missing rank must not hang the GPU.
+__global__ void __launch_bounds__(32) peer_barrier_kernel(DetectArgs a) {
+    const uint32_t p = threadIdx.x;
+    // the step number lives in device memory (word 31 of this rank's flag buffer), so a captured CUDA graph that is
+    // replayed still counts; every rank runs the same number of steps
+    uint32_t epoch = 0;
+    if (p == 0) {
+        epoch = a.peer_flag[a.rank][31] + 1u;
+        a.peer_flag[a.rank][31] = epoch;
+    }
+    epoch = __shfl_sync(FULL, epoch, 0);
+    if (p >= a.n_peers) return;
+    __threadfence_system();  // the ordering kernel's peer stores before the flag
+    uint32_t *theirs = a.peer_flag[p] + a.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+    const uint32_t *mine = a.peer_flag[a.rank] + p;
+    uint32_t seen = 0;
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        if ((int32_t)(seen - epoch) >= 0) break;
+        __nanosleep(100);
+    }
+    if ((int32_t)(seen - epoch) < 0) atomicAdd(a.counters + kCntPeerTimeout, 1u);
 }
 
 // FromReport path: bad regions are given, only type_of_read (editor/mod.rs:85-100) runs. One thread
@@ -1084,6 +1116,10 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     ++launches;
     order_kernel<<<w.n_parts, kPartRows, 0, stream>>>(a, w, not_coverage);
     ++launches;
+    if (a.n_peers) {
+        peer_barrier_kernel<<<1, 32, 0, stream>>>(a);
+        ++launches;
+    }
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
 }

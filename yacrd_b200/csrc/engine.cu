@@ -137,6 +137,11 @@ struct yb_ctx {
     PinnedBuf<yb::DevRowStats> h_rowstats;
     uint8_t *ext_bitmap = nullptr;  // yb_bind_device_bitmap
     size_t ext_bitmap_bytes = 0;
+    // peer-memory all-gather (yb_bind_peers)
+    uint32_t n_peers = 0, peer_rank = 0;
+    size_t peer_slot_bytes = 0;
+    uint8_t *peer_gather[YB_MAX_PEERS] = {};
+    uint32_t *peer_flags[YB_MAX_PEERS] = {};
 
     // ---- results (pinned host) ----
     PinnedBuf<uint8_t> h_cls, h_bitmap;
@@ -757,6 +762,17 @@ int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *s
         a.scratch_bytes = c->d_scratch.cap;
         if (c->ext_bitmap && c->ext_bitmap_bytes < c->bitmap_bytes())
             return c->fail(YB_ERR_INVALID_ARGUMENT, "bound bitmap buffer too small (%zu < %zu bytes)", c->ext_bitmap_bytes, c->bitmap_bytes());
+        a.n_peers = c->n_peers;
+        if (c->n_peers) {
+            if (c->peer_slot_bytes < c->bitmap_bytes())
+                return c->fail(YB_ERR_INVALID_ARGUMENT, "peer slot too small (%zu < %zu bytes)", c->peer_slot_bytes, c->bitmap_bytes());
+            a.rank = c->peer_rank;
+            for (uint32_t p = 0; p < c->n_peers; ++p) {
+                a.peer_slot[p] = c->peer_gather[p] + (size_t)c->peer_rank * c->peer_slot_bytes;
+                a.peer_flag[p] = c->peer_flags[p];
+            }
+            a.bitmap = a.peer_slot[c->peer_rank];
+        }
         launches = yb::launch_detect(a, coverage > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)coverage, not_coverage, st);
     }
     if (launches < 0) return c->cuda_fail(cudaGetLastError(), "kernel launch");
@@ -787,13 +803,17 @@ int yb_download(yb_ctx *c) {
     YB_CUDA(c, cudaMemcpyAsync(c->h_gap_ptr.p, c->d_gap_ptr.p, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, c->stream));
     if (n) {
         YB_CUDA(c, cudaMemcpyAsync(c->h_cls.p, c->d_cls.p, n, cudaMemcpyDeviceToHost, c->stream));
-        YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p, c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p, c->bitmap_bytes(), cudaMemcpyDeviceToHost, c->stream));
+        const uint8_t *bm = c->n_peers && !c->from_report ? c->peer_gather[c->peer_rank] + (size_t)c->peer_rank * c->peer_slot_bytes
+                                                         : (c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p);
+        YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p, bm, c->bitmap_bytes(), cudaMemcpyDeviceToHost, c->stream));
     }
     YB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->h_counters.p[yb::kCntMalformed])
         return c->fail(YB_ERR_MALFORMED_INTERVAL,
                        "%u interval(s) violate 0 <= begin < end <= length; the reference's result is undefined for them",
                        c->h_counters.p[yb::kCntMalformed]);
+    if (c->h_counters.p[yb::kCntPeerTimeout])
+        return c->fail(YB_ERR_STATE, "peer all-gather: %u rank(s) never signalled this step", c->h_counters.p[yb::kCntPeerTimeout]);
     if (c->h_counters.p[yb::kCntStageOverflow])
         return c->fail(YB_ERR_STATE, "internal error: bad-region staging buffer overflow (%u reads)", c->h_counters.p[yb::kCntStageOverflow]);
     c->n_gaps = c->h_gap_ptr.p[n];
@@ -833,6 +853,69 @@ int yb_bind_device_bitmap(yb_ctx *c, void *device_ptr, size_t n_bytes) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
     c->ext_bitmap = static_cast<uint8_t *>(device_ptr);
     c->ext_bitmap_bytes = device_ptr ? n_bytes : 0;
+    return YB_OK;
+}
+
+void *yb_peer_alloc(yb_ctx *c, size_t n_bytes, void *handle_out) {
+    if (!c || c->host_only || !handle_out || n_bytes == 0) return nullptr;
+    static_assert(sizeof(cudaIpcMemHandle_t) == YB_IPC_HANDLE_BYTES, "handle size");
+    if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+    void *p = nullptr;
+    cudaIpcMemHandle_t h;
+    if (cudaMalloc(&p, n_bytes) != cudaSuccess || cudaMemset(p, 0, n_bytes) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+        c->cuda_fail(cudaGetLastError(), "yb_peer_alloc");
+        if (p) cudaFree(p);
+        return nullptr;
+    }
+    memcpy(handle_out, &h, sizeof h);
+    return p;
+}
+
+void *yb_peer_open(yb_ctx *c, const void *handle) {
+    if (!c || c->host_only || !handle) return nullptr;
+    if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        c->cuda_fail(cudaGetLastError(), "cudaIpcOpenMemHandle");
+        return nullptr;
+    }
+    return p;
+}
+
+int yb_peer_close(yb_ctx *c, void *mapped) {
+    if (!c || !mapped) return YB_ERR_INVALID_ARGUMENT;
+    YB_CUDA(c, cudaSetDevice(c->device));
+    YB_CUDA(c, cudaStreamSynchronize(c->stream));
+    YB_CUDA(c, cudaIpcCloseMemHandle(mapped));
+    return YB_OK;
+}
+
+int yb_peer_free(yb_ctx *c, void *allocated) {
+    if (!c || !allocated) return YB_ERR_INVALID_ARGUMENT;
+    YB_CUDA(c, cudaSetDevice(c->device));
+    YB_CUDA(c, cudaStreamSynchronize(c->stream));
+    YB_CUDA(c, cudaFree(allocated));
+    return YB_OK;
+}
+
+int yb_bind_peers(yb_ctx *c, void *const *gather_bufs, void *const *flag_bufs, uint32_t n_ranks, uint32_t rank, size_t slot_bytes) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (n_ranks == 0) {
+        c->n_peers = 0;
+        return YB_OK;
+    }
+    if (!gather_bufs || !flag_bufs || n_ranks > YB_MAX_PEERS || rank >= n_ranks || (slot_bytes & 3u))
+        return c->fail(YB_ERR_INVALID_ARGUMENT, "yb_bind_peers: at most %d ranks, rank < n_ranks, slot_bytes a multiple of 4", YB_MAX_PEERS);
+    for (uint32_t p = 0; p < n_ranks; ++p) {
+        if (!gather_bufs[p] || !flag_bufs[p]) return c->fail(YB_ERR_INVALID_ARGUMENT, "yb_bind_peers: null buffer for rank %u", p);
+        c->peer_gather[p] = static_cast<uint8_t *>(gather_bufs[p]);
+        c->peer_flags[p] = static_cast<uint32_t *>(flag_bufs[p]);
+    }
+    c->n_peers = n_ranks;
+    c->peer_rank = rank;
+    c->peer_slot_bytes = slot_bytes;
     return YB_OK;
 }
 

@@ -26,6 +26,7 @@ enum Counter : uint32_t {
     kCntStage = 11,      // bump allocator (in pairs) of the bad-region staging buffer
     kCntTileSlow = 12,   // dynamic tile scheduler of the generic (u32) pass
     kCntStageOverflow = 14,  // rows whose bad regions did not fit the staging buffer (must stay 0)
+    kCntPeerTimeout = 15,  // the peer barrier gave up waiting (a rank died or never launched)
     kCntTicket = 13,     // order_kernel: dynamic part index (decoupled look-back needs in-order starts)
     kCntClassCursor = 16,  // kNumClasses cursors of the worklist scatter
     kCntHist = 48,         // kHistSlots x {NotBad, Chimeric, NotCovered}: the detect step's class histogram, striped
@@ -78,6 +79,10 @@ struct DetectArgs {
     uint32_t *gap_ptr;       // n_reads + 1: exclusive scan of per-read bad-region counts
     uint2 *gaps;             // CSR of bad regions, capacity n_iv + n_reads
     uint8_t *bitmap;         // ceil(n_reads / 4) bytes rounded up to 4, 2 bits per read
+    // peer-memory all-gather (n_peers == 0: off): this rank's slot in every rank's gather buffer, every rank's flags
+    uint32_t n_peers, rank;
+    uint8_t *peer_slot[16];  // peer p's gather buffer + rank * slot_bytes
+    uint32_t *peer_flag[16]; // peer p's flag array (word q: last step rank q finished; word 31: own step counter)
     uint32_t *counters;      // kNumCounters
     // scratch
     void *scratch;

@@ -81,3 +81,63 @@ def global_classes(gathered, n_reads, n_shards):
         m = sh == s
         out[m] = cl[local[m]]
     return out
+
+
+class PeerGather:
+    """All-gather of the class bitmap fused into the kernels' epilogue over NVLink peer memory (include/yacrd_b200.h,
+    "peer-memory all-gather"): every rank allocates one gather buffer [world x slot_bytes] and one flag buffer, the CUDA
+    IPC handles travel through torch.distributed (any backend), every rank maps every other rank's buffers, and from
+    then on `ctx.compute_device()` leaves all ranks' bitmaps in every rank's buffer — no separate collective."""
+
+    def __init__(self, ctx, slot_bytes, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _native as N
+        self.ctx, self.slot_bytes = ctx, int(slot_bytes)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 16:
+            raise ValueError("PeerGather supports at most 16 ranks")
+        L = ctx._L
+        hg, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+        self._own_gather = L.yb_peer_alloc(ctx._h, self.world * self.slot_bytes, hg)
+        self._own_flags = L.yb_peer_alloc(ctx._h, 128, hf)
+        if not self._own_gather or not self._own_flags:
+            raise N.YacrdError(-12, L.yb_last_error(ctx._h).decode())
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (hg.raw, hf.raw), group=group)
+        self._mapped = []
+        gather, flags = [], []
+        for p, (g, f) in enumerate(handles):
+            if p == self.rank:
+                gather.append(self._own_gather)
+                flags.append(self._own_flags)
+                continue
+            pg, pf = L.yb_peer_open(ctx._h, g), L.yb_peer_open(ctx._h, f)
+            if not pg or not pf:
+                raise N.YacrdError(-12, L.yb_last_error(ctx._h).decode())
+            self._mapped += [pg, pf]
+            gather.append(pg)
+            flags.append(pf)
+        ga = (C.c_void_p * self.world)(*gather)
+        fa = (C.c_void_p * self.world)(*flags)
+        ctx._ck(L.yb_bind_peers(ctx._h, ga, fa, self.world, self.rank, self.slot_bytes))
+        dist.barrier(group=group)  # nobody starts writing before everybody has mapped
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.world, self.slot_bytes), "typestr": "|u1", "data": (int(self._own_gather), False), "version": 2}
+
+    def tensor(self):
+        """This rank's gather buffer as a [world, slot_bytes] uint8 torch tensor (a view, no copy)."""
+        import torch
+        return torch.as_tensor(self, device="cuda")
+
+    def close(self):
+        L = self.ctx._L
+        if getattr(self, "_own_gather", None) and self.ctx._h:
+            L.yb_bind_peers(self.ctx._h, None, None, 0, 0, 0)
+            for m in self._mapped:
+                L.yb_peer_close(self.ctx._h, m)
+            L.yb_peer_free(self.ctx._h, self._own_gather)
+            L.yb_peer_free(self.ctx._h, self._own_flags)
+        self._own_gather = None
