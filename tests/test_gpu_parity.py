@@ -212,6 +212,27 @@ def test_fuzz_small_reads_every_register_tier(c):
         assert_same_as_oracle(rowptr, iv, length, c, n)
 
 
+@pytest.mark.parametrize("rl_max", [0, 64, 128])
+@pytest.mark.parametrize("c", [0, 1, 3, 4, 7, 8, 30, 63, 64, 127, 5000, 2**32 - 1])
+def test_row_per_lane_tier_every_slot_class_boundary(c, rl_max, monkeypatch):
+    """Rows of every k in 0..140 through the opt-in row-per-lane tier (YB_RL_MAX_SLOTS: packed rows with
+    k + min(c, k) + 1 <= rl_max key slots, in slot classes of 8) and through the default lane-group tier (rl_max = 0):
+    every class boundary, the hand-over between the tiers, short and 16-bit-limit lengths."""
+    monkeypatch.setenv("YB_RL_MAX_SLOTS", str(rl_max))
+    rng = random.Random(4242 + c % 1000)
+    rowptr, iv, length = _random_csr(rng, 141 * 40, list(range(141)), [1, 5, 40, 3000, 65534, 65535])
+    # every k really occurs at least once, in this order, behind the random rows
+    rp2, iv2, len2 = _random_csr(random.Random(7), 141, [0], [1000])
+    rows = [[(rng.randrange(0, 900), 1000 - rng.randrange(0, 90)) for _ in range(k)] for k in range(141)]
+    rp2 = np.zeros(142, dtype=np.uint32)
+    rp2[1:] = np.cumsum([len(r) for r in rows])
+    iv2 = np.array([p for r in rows for p in r], dtype=np.uint32).reshape(-1, 2)
+    rowptr = np.concatenate([rowptr, rowptr[-1] + rp2[1:]]).astype(np.uint32)
+    iv = np.concatenate([iv, iv2])
+    length = np.concatenate([length, len2]).astype(np.uint32)
+    assert_same_as_oracle(rowptr, iv, length, c, 0.4)
+
+
 def test_fuzz_tiny_positions_many_ties():
     rng = random.Random(5)
     rowptr, iv, length = _random_csr(rng, 20000, [1, 2, 3, 5, 8, 13, 21, 40], [1, 2, 3, 4, 5, 6, 9])
@@ -241,6 +262,21 @@ def test_empty_context_and_reads_without_intervals():
     iv = np.array([[5, 9]], dtype=np.uint32)
     length = np.array([100, 0, 10, 7], dtype=np.uint32)
     assert_same_as_oracle(rowptr, iv, length, 0, 0.8)
+
+
+@pytest.mark.parametrize("rl_max", [64, 128])
+def test_row_per_lane_tier_synthetic_and_golden(rl_max, monkeypatch, tmp_path):
+    """The opt-in row-per-lane tier on the golden PAF and on a synthetic shard, bit-exact like the default tier."""
+    monkeypatch.setenv("YB_RL_MAX_SLOTS", str(rl_max))
+    fm = yb.FullMemory()
+    fm.init(os.path.join(GOLDEN, "c1_overlaps.paf"))
+    bp = yb.FromOverlap(fm, 0, 0.8)
+    bp.compute_all_bad_part()
+    assert sorted(bp.report_lines()) == read_sorted_lines(os.path.join(GOLDEN, "c1_truth.sorted.yacrd"))
+    fm.close()
+    csr = yb.synth_csr(60000, 50)
+    for c, n in ((4, 0.4), (0, 0.8)):
+        assert_same_as_oracle(csr.rowptr, csr.iv, csr.length, c, n)
 
 
 def test_config2_100k_reads_c0():

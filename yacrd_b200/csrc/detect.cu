@@ -37,6 +37,8 @@
 //   order_kernel     single pass over the rows: scan of the per-row counts (decoupled look-back over cheap,
 //                    uniform parts), staging -> ordered bad-region CSR, classification, 2-bit bitmap, histogram.
 #include "pileup.cuh"
+#include "sortnets.cuh"
+#include <cstdlib>
 
 namespace yb {
 namespace {
@@ -101,6 +103,15 @@ struct ClassTab {
     uint32_t inv[kNumClasses];            // ceil(65536 / G): x / G == (x * inv) >> 16 for x < 2048
 };
 
+// Row-per-lane tier: where each slot class's records sit in the worklist and how its batches (32 rows) are numbered.
+// Classes are processed largest first: the small kernel walks N = 64, 56, ..., 8, the mid kernel N = 128, ..., 72.
+struct RLTab {
+    uint32_t entry_base[kNumRL];
+    uint32_t count[kNumRL];
+    uint32_t item_base_small[kNumRL / 2 + 1];  // batches before the q-th class of the small kernel
+    uint32_t item_base_mid[kNumRL / 2 + 1];
+};
+
 // scratch carve-up
 struct Work {
     uint4 *recs;                     // n_reads worklist records {row, first interval, k | class << 16 | valid, len}
@@ -117,20 +128,21 @@ struct Work {
 // ------------------------------------------------------------------------------------------------
 // scatter_kernel: rows -> worklist records grouped by size class (CTA-aggregated cursors)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Work w, ClassTab tab) {
-    __shared__ uint32_t s_cnt[kNumClasses], s_base[kNumClasses];
+__global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Work w, ClassTab tab, RLTab rl, uint32_t c, uint32_t rl_max) {
+    __shared__ uint32_t s_cnt[kNumAllClasses], s_base[kNumAllClasses];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * kScatterRows + tid;
-    if (tid < (uint32_t)kNumClasses) s_cnt[tid] = 0u;
+    if (tid < (uint32_t)kNumAllClasses) s_cnt[tid] = 0u;
     if (tid < kScatterRows / kPartRows && blockIdx.x * (kScatterRows / kPartRows) + tid < w.n_parts)
         w.part_total[blockIdx.x * (kScatterRows / kPartRows) + tid] = 0u;
     __syncthreads();
-    int cls = -2;
+    int cls = -2;  // 0 .. kNumClasses-1: lane-group classes; kNumClasses + q: row-per-lane slot class q; -1: big row
     uint32_t p0 = 0, k = 0, len = 0;
     if (r < a.n_reads) {
         p0 = __ldg(a.rowptr + r);
         k = __ldg(a.rowptr + r + 1) - p0;
         len = __ldg(a.len + r);
-        cls = class_of_row(k, len);
+        const int q = rl_class_of_row(k, len, c, rl_max);
+        cls = q >= 0 ? kNumClasses + q : class_of_row(k, len);
         if (cls < 0) {
             const uint32_t j = atomicAdd(a.counters + kCntBigList, 1u);
             w.big_list[j] = r;
@@ -142,10 +154,12 @@ __global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Wor
     if (cls >= 0 && lane == leader) wbase = atomicAdd(&s_cnt[cls], (uint32_t)__popc(peers));
     wbase = __shfl_sync(FULL, wbase, leader);
     __syncthreads();
-    if (tid < (uint32_t)kNumClasses && s_cnt[tid]) s_base[tid] = atomicAdd(a.counters + kCntClassCursor + tid, s_cnt[tid]);
+    if (tid < (uint32_t)kNumAllClasses && s_cnt[tid]) s_base[tid] = atomicAdd(a.counters + kCntClassCursor + tid, s_cnt[tid]);
     __syncthreads();
-    if (cls >= 0)
-        w.recs[tab.entry_base[cls] + s_base[cls] + wbase + rank] = make_uint4(r, p0, k | ((uint32_t)cls << 16) | kRecValid, len);
+    if (cls >= 0) {
+        const uint32_t eb = cls < kNumClasses ? tab.entry_base[cls] : rl.entry_base[cls - kNumClasses];
+        w.recs[eb + s_base[cls] + wbase + rank] = make_uint4(r, p0, k | ((uint32_t)(cls < kNumClasses ? cls : 0) << 16) | kRecValid, len);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -527,7 +541,7 @@ __device__ __forceinline__ LaneGeo lane_geo(const ClassTab &tab, uint32_t cls) {
 // into bad regions and appends the batch's regions to the staging buffer.
 template <bool PK>
 __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w, WarpSmem &ws, uint2 *buf, const LaneGeo geo,
-                                              const uint4 rec, uint32_t c, uint32_t &malformed, uint2 &chunk) {
+                                              const uint4 rec, uint32_t c, uint2 &chunk) {
     const uint32_t lane = lane_id();
     const uint32_t G = geo.G, g = geo.g;
     const bool valid = geo.in_group && (rec.z & kRecValid);
@@ -536,9 +550,7 @@ __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w
     // striped load (conflict-free); the initial arrangement is irrelevant to the sort
     uint32_t K0[E];             // PK: begin | end << 16; else begins
     uint32_t K1[PK ? 1 : E];    // else ends
-    // validity 0 <= b < e <= len: one compare per interval for b < e, a running maximum of the ends for e <= len
-    bool bad_iv = false;
-    uint32_t emax = 0;
+    // (validity 0 <= b < e <= len is tested once per upload by launch_validate, not at every detect step)
     const uint2 *lane_iv = slot + g;           // this lane's elements: g, g + G, g + 2G, ...
     const uint32_t left = k > g ? k - g : 0u;  // element t exists iff t * G < left
     auto load16 = [&](const uint32_t GG) {     // GG: the batch's G as a compile-time constant where it is a common one
@@ -547,8 +559,6 @@ __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w
             uint2 v = make_uint2(INF, INF);
             if ((uint32_t)t * GG < left) {
                 v = lane_iv[(uint32_t)t * GG];
-                bad_iv |= v.x >= v.y;
-                emax = max(emax, v.y);
             }
             if (PK) {
                 K0[t] = __byte_perm(v.x, v.y, 0x5410);
@@ -568,7 +578,6 @@ __device__ __forceinline__ void process_batch(const DetectArgs &a, const Work &w
         case 8: load16(8); break;
         default: load16(G); break;
     }
-    malformed += (bad_iv || emax > len) ? 1u : 0u;
     if (PK) {
         sort_group<PK>(K0, G, g, geo.in_group);
     } else {
@@ -752,7 +761,7 @@ __global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(De
     }
     __syncwarp();
     const uint32_t n_items = tab.item_base[kNumClasses];
-    uint32_t q = 0, malformed = 0;
+    uint32_t q = 0;
     // Dynamic schedule (batches cost between 0.3 and 2 us): a warp draws batch indices from one counter, three
     // batches ahead, so the atomic's latency hides behind a whole batch. Indices drawn by a warp only grow.
     auto draw_raw = [&]() {  // lane 0 holds the index; nobody waits for the atomic until the value is broadcast
@@ -775,8 +784,8 @@ __global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(De
         uint2 *buf = buf0 + b * kBufIntervals;
         mbar_wait(&ws.mbar[b], parity);
         const LaneGeo geo = lane_geo(tab, cls0);
-        if (cls0 < (uint32_t)kNumG) process_batch<true>(a, w, ws, buf, geo, rec0, c, malformed, chunk);
-        else process_batch<false>(a, w, ws, buf, geo, rec0, c, malformed, chunk);
+        if (cls0 < (uint32_t)kNumG) process_batch<true>(a, w, ws, buf, geo, rec0, c, chunk);
+        else process_batch<false>(a, w, ws, buf, geo, rec0, c, chunk);
         // generic-proxy accesses of this batch (crossings written into the slab) before the async-proxy refill
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -791,11 +800,266 @@ __global__ void __launch_bounds__(kSortThreads, YB_SORT_MIN_CTAS) sort_kernel(De
         parity ^= b;
         b ^= 1u;
     }
-    malformed = warp_sum(malformed);
-    if (lane == 0 && malformed) atomicAdd(a.counters + kCntMalformed, malformed);
 }
 
 constexpr size_t kSortSmemBytes = kWarpSmemBytes * kSortWarps;
+
+// ------------------------------------------------------------------------------------------------
+// row-per-lane tier (rl_kernel): packed rows of at most 128 key slots, ONE lane per row, 32 rows of one slot class per
+// warp. Everything the lane-group tier pays for sharing a row between lanes disappears: no shuffles and no
+// predicated exchanges in the sort (a straight-line merge-exchange network over the N registers of the lane,
+// sortnets.cuh), no per-group bookkeeping replicated G times, and the crossing tests index registers only.
+//
+// Sentinel ends. The closed form compares B_i with E[i-c-1] and E[i-c]: a shift by the run-time threshold c in RANK
+// space. The two halves of a packed key are sorted independently, so the shift is done by the sort itself: c' + 1
+// extra keys (begin = +inf, end = 0), c' = min(c, k), are added to the row. After the sort the high halves are
+// E'_i = E[i - c' - 1] (0 below the first end, exactly the convention E[-1] = 0), hence
+//     a_i = V1_i  = (E'_i     <= B_i)        b_i = !V0_i = (B_i < E'_{i+1})
+//     up-crossing at begin i = a_i & b_i,    down-crossing (value E'_{i+1}) = b_i & a_{i+1},
+// all with compile-time register indices. Pushing a_0, !b_0, a_1, !b_1, ... into one bit string Z (most significant
+// first) makes the crossings, in the order U0 D0 U1 D1 ... of the bad-region list, the set bits of Z & (Z << 1).
+// (c >= k behaves like c = k: the depth never exceeds k.)
+//
+// Staging. A warp-instruction of this tier serves 32 rows, so the kernel lives on occupancy (measured: about 0.12
+// instructions per clock per resident warp, whatever the tier), and occupancy is shared memory: the batch is
+// therefore staged PACKED and TRANSPOSED, Tp[slot][row] with a pitch of 33 words (4 bytes per interval instead of
+// 8; 8.4 KB per warp for 64 slots). The warp walks the 32 rows, one coalesced 8-byte load per lane and row, packs
+// (PRMT) and stores conflict-free; afterwards lane j reads its row down column j, conflict-free again, with
+// immediate offsets. The sorted keys go back into the same column (the crossing VALUES are fetched from there by
+// run-time index). cp.async / TMA would keep 8 bytes per interval in shared memory and cost more issue slots per row
+// (LDGSTS: three dummy LDS per copy on sm_100a; UBLKCP: an ELECT / R2UR loop).
+// Interval validity (0 <= b < e <= len) is not re-tested here: launch_validate does it once per upload.
+// ------------------------------------------------------------------------------------------------
+#ifndef YB_RL_WARPS_SMALL
+#define YB_RL_WARPS_SMALL 4
+#endif
+#ifndef YB_RL_WARPS_MID
+#define YB_RL_WARPS_MID 4
+#endif
+#ifndef YB_RL_MIN_CTAS_SMALL
+#define YB_RL_MIN_CTAS_SMALL 5
+#endif
+#ifndef YB_RL_MIN_CTAS_MID
+#define YB_RL_MIN_CTAS_MID 3
+#endif
+constexpr uint32_t kTpPitch = 33;  // words between consecutive slots of Tp
+// per warp: Tp (nmax slots + the +inf key behind the last one) and the 32 copy descriptors
+__host__ __device__ constexpr size_t rl_tp_bytes(uint32_t nmax) { return ((nmax + 1u) * kTpPitch * sizeof(uint32_t) + 15u) & ~(size_t)15; }
+__host__ __device__ constexpr size_t rl_warp_smem(uint32_t nmax) { return rl_tp_bytes(nmax) + 32u * sizeof(uint2); }
+
+// Transposing copy of the batch's rows into Tp: row j's interval t -> Tp[t][j] as begin | end << 16.
+// desc[j] = {first interval, k} of row j, read back as broadcasts. CH = 32-interval chunks a row of the class can have.
+template <int CH>
+__device__ __forceinline__ void rl_stage(const DetectArgs &a, uint32_t *Tp, const uint2 *desc) {
+    constexpr int RB = CH <= 2 ? 8 : 4;  // rows whose loads are in flight together (the loads of a group are issued
+                                         // before any of its stores: shared-memory stores would otherwise fence the
+                                         // next descriptor read and serialise the rows on the load latency)
+    const uint32_t lane = lane_id();
+    const uint2 *src_lane = a.iv + lane;
+    uint32_t *dst_lane = Tp + lane * kTpPitch;
+#pragma unroll 1
+    for (int j0 = 0; j0 < 32; j0 += RB) {
+        uint2 d[RB], v[RB][CH];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) d[r] = desc[j0 + r];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch) {
+                v[r][ch] = make_uint2(0u, 0u);
+                if (lane + 32u * ch < d[r].y) v[r][ch] = __ldg(src_lane + d[r].x + 32 * ch);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+#pragma unroll
+            for (int ch = 0; ch < CH; ++ch)
+                if (lane + 32u * ch < d[r].y) dst_lane[32 * ch * kTpPitch + j0 + r] = __byte_perm(v[r][ch].x, v[r][ch].y, 0x5410);
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void rl_batch(const DetectArgs &a, const Work &w, uint32_t *Tp, uint2 *desc, const uint4 rec, uint32_t c,
+                                         uint2 &chunk) {
+    constexpr int W = N / 16 + ((N % 16) ? 1 : 0);  // 32-bit words of Z: 16 slots each
+    const uint32_t lane = lane_id();
+    const bool valid = (rec.z & kRecValid) != 0u;
+    const uint32_t k = valid ? (rec.z & 0xFFFFu) : 0u, len = rec.w;
+    const uint32_t cp = min(c, k);
+    desc[lane] = make_uint2(rec.y, k);
+    __syncwarp();
+    rl_stage<(N + 31) / 32>(a, Tp, desc);
+    uint32_t *col = Tp + lane;  // the lane's row: slot t at col[t * kTpPitch]
+    // sentinels behind the row's intervals: c' + 1 keys (+inf, 0), then (+inf, +inf)
+    for (uint32_t t = k; t < (uint32_t)N; ++t) col[t * kTpPitch] = t <= k + cp ? 0x0000FFFFu : FULL;
+    __syncwarp();
+    uint32_t K[N + 1];
+#pragma unroll
+    for (int t = 0; t < N; ++t) K[t] = col[t * kTpPitch];
+    K[N] = FULL;
+    {
+        uint32_t(&Ks)[N] = *reinterpret_cast<uint32_t(*)[N]>(&K[0]);
+        SortNet<N>::run(Ks, [](uint32_t &x, uint32_t &y) {
+            const uint32_t lo = __vminu2(x, y), hi = __vmaxu2(x, y);
+            x = lo;
+            y = hi;
+        });
+    }
+    // the sorted keys go back to the lane's column: crossing VALUES are fetched from there by run-time index
+#pragma unroll
+    for (int t = 0; t <= N; ++t) col[t * kTpPitch] = K[t];
+    // Z: a_i at bit 31 - 2t, !b_i at bit 30 - 2t of word i / 16 (t = i % 16); X = crossings, in bad-region order
+    uint32_t X[W];
+    uint32_t m = 0;
+    {
+        uint32_t Z[W + 1];
+#pragma unroll
+        for (int wd = 0; wd < W; ++wd) {
+            uint32_t z = 0;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int i = 16 * wd + t;
+                if (i < N) {
+                    const uint32_t q = __byte_perm(K[i], FULL, 0x1044);  // B_i << 16 | 0xFFFF: key <= q  <=>  end half <= B_i
+                    z = push_le(z, K[i], q);
+                    z = push_le(z, K[i + 1], q);
+                } else {
+                    z <<= 2;
+                }
+            }
+            Z[wd] = z ^ 0x55555555u;
+        }
+        Z[W] = 0u;
+#pragma unroll
+        for (int wd = 0; wd < W; ++wd) {
+            X[wd] = valid ? (Z[wd] & __funnelshift_l(Z[wd + 1], Z[wd], 1)) : 0u;
+            m += __popc(X[wd]);
+        }
+    }
+    if (m & 1u) m = 0;  // only malformed rows (already reported at upload): treated as "never above c"
+    // staging: a row reserves an upper bound (m / 2 + 1 regions: whether the list starts at 0 / ends at len is only known
+    // once the first / last crossing VALUE is read); order_kernel copies the ng regions actually written.
+    // The warp owns a chunk of the staging buffer and refills it with one atomic when it runs out.
+    const uint32_t ub = valid ? (m ? (m >> 1) + 1u : (len != 0u ? 1u : 0u)) : 0u;
+    const uint32_t inc = warp_incl_scan(ub);
+    const uint32_t total = __shfl_sync(FULL, inc, 31);
+    uint32_t base;
+    if (total <= chunk.y - chunk.x) {
+        base = chunk.x;
+        chunk.x += total;
+    } else {
+        const bool direct = total >= kStageChunk / 4u;  // a large batch takes exactly what it needs
+        uint32_t got = 0;
+        if (lane == 0) got = atomicAdd(a.counters + kCntStage, direct ? total : kStageChunk);
+        base = __shfl_sync(FULL, got, 0);
+        if (!direct) chunk = make_uint2(base + total, base + kStageChunk);
+    }
+    base += inc - ub;
+    if (valid && (uint64_t)base + ub > w.stage_cap) {  // cannot happen with the capacity the engine allocates; never write outside
+        atomicAdd(a.counters + kCntStageOverflow, 1u);
+        m = 0;
+        base = 0xFFFFFFFFu;
+    }
+    // flat list [0 if h] U0 D0 U1 D1 ... [len if tail], minus U0 when U0 == 0 (h false), minus D_last when D_last == len:
+    // crossing j goes to flat position j + off, off = +1 (h) or -1 (!h); position -1 (U0 == 0) is simply not written
+    uint32_t *F = reinterpret_cast<uint32_t *>(w.stage + (base == 0xFFFFFFFFu ? 0u : base));
+    uint32_t off = 1u, j = 0, v = 0;
+    if (m) F[0] = 0u;
+#pragma unroll
+    for (int wd = 0; wd < W; ++wd) {
+        uint32_t x = m ? X[wd] : 0u;
+        while (x) {
+            const uint32_t p = __clz(x);
+            x &= ~(0x80000000u >> p);
+            const uint32_t i = 16u * wd + ((p + 1u) >> 1);  // up-crossing: B_i; down-crossing: E'_{i+1}
+            v = (col[i * kTpPitch] >> (16u * (p & 1u))) & 0xFFFFu;
+            if (j == 0u && v == 0u) off = 0xFFFFFFFFu;
+            const uint32_t pos = j + off;
+            if (pos != 0xFFFFFFFFu) F[pos] = v;
+            ++j;
+        }
+    }
+    if (valid) {
+        uint32_t ng = 0;
+        if (m) {  // v = D_last: the list ends with (D_last, len) unless D_last == len
+            const uint32_t flat = m + off + (v != len ? 1u : 0xFFFFFFFFu);
+            if (v != len) F[m + off] = len;
+            ng = flat >> 1;
+        } else if (base != 0xFFFFFFFFu && len != 0u) {  // depth never above c: one region (0, len)
+            F[0] = 0u;
+            F[1] = len;
+            ng = 1u;
+        }
+        a.gap_ptr[rec.x] = ng;  // count for now; order_kernel turns it into the offset
+        w.soff[rec.x] = base == 0xFFFFFFFFu ? 0u : base;
+        if (ng) atomicAdd(w.part_total + (rec.x >> kPartShift), ng);
+    }
+}
+
+template <bool MID>
+__global__ void __launch_bounds__(32 * (MID ? YB_RL_WARPS_MID : YB_RL_WARPS_SMALL), MID ? YB_RL_MIN_CTAS_MID : YB_RL_MIN_CTAS_SMALL)
+    rl_kernel(DetectArgs a, Work w, RLTab tab, uint32_t c) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr uint32_t NMAX = MID ? kRLMaxSlots : kRLSmallSlots;
+    constexpr int NQ = kNumRL / 2;
+    const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
+    uint32_t *Tp = reinterpret_cast<uint32_t *>(smem_raw + wid * rl_warp_smem(NMAX));
+    uint2 *desc = reinterpret_cast<uint2 *>(smem_raw + wid * rl_warp_smem(NMAX) + rl_tp_bytes(NMAX));
+    const uint32_t *item_base = MID ? tab.item_base_mid : tab.item_base_small;
+    const uint32_t n_items = item_base[NQ];
+    // Static schedule: warp g of the grid takes batches g, g + G, g + 2 G, ... Batches of one class cost the same and the
+    // classes are walked largest first, so the warps stay within one batch of each other; warps never synchronise.
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t q = 0;
+    // the q-th class in processing order has N = NMAX - 8 q slots: slot class index N / 8 - 1
+    auto load_rec = [&](uint32_t item, uint32_t &nslots) {
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        nslots = 8u;
+        if (item >= n_items) return rec;
+        while (item >= item_base[q + 1]) ++q;
+        nslots = NMAX - 8u * q;
+        const uint32_t cl = nslots / 8u - 1u;
+        const uint32_t e = (item - item_base[q]) * 32u + lane;
+        if (e < tab.count[cl]) rec = __ldg(w.recs + tab.entry_base[cl] + e);
+        return rec;
+    };
+    uint32_t item = blockIdx.x * (blockDim.x >> 5) + wid;
+    uint32_t n0, n1, n2;
+    uint4 rec0 = load_rec(item, n0);
+    uint4 rec1 = load_rec(item + n_warps, n1);
+    uint2 chunk = make_uint2(0, 0);  // [next free pair, end) of the warp's staging chunk
+    while (item < n_items) {
+        const uint4 rec2 = load_rec(item + 2u * n_warps, n2);  // in flight behind this batch
+        // the next batch's rows are pulled into L2 while this one is sorted (lane j touches the 128-byte lines of its
+        // own next row): the staging loads of the next batch then pay an L2 hit instead of a DRAM access
+        if (rec1.z & kRecValid) {
+            const char *p = reinterpret_cast<const char *>(a.iv + rec1.y);
+            const char *e = p + 8u * (rec1.z & 0xFFFFu);
+            for (p = reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127); p < e; p += 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+#define YB_RL_CASE(NN) case NN: rl_batch<NN>(a, w, Tp, desc, rec0, c, chunk); break;
+        if (MID) {
+            switch (n0) {
+                YB_RL_CASE(72) YB_RL_CASE(80) YB_RL_CASE(88) YB_RL_CASE(96) YB_RL_CASE(104) YB_RL_CASE(112) YB_RL_CASE(120)
+                default: rl_batch<128>(a, w, Tp, desc, rec0, c, chunk); break;
+            }
+        } else {
+            switch (n0) {
+                YB_RL_CASE(8) YB_RL_CASE(16) YB_RL_CASE(24) YB_RL_CASE(32) YB_RL_CASE(40) YB_RL_CASE(48) YB_RL_CASE(56)
+                default: rl_batch<64>(a, w, Tp, desc, rec0, c, chunk); break;
+            }
+        }
+#undef YB_RL_CASE
+        __syncwarp();  // every lane is done with its column before the next batch is staged
+        rec0 = rec1;
+        rec1 = rec2;
+        n0 = n1;
+        n1 = n2;
+        item += n_warps;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // ordering pass: the sorting kernels left, per row, a count and a staging offset, and per part of 256 rows the
@@ -953,9 +1217,10 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint32_t *__restric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ len,
                                                           uint32_t n_reads, DevRowStats *out) {
-    __shared__ uint32_t s_cnt[kNumClasses + 1], s_max, s_bad[3];
+    __shared__ uint32_t s_cnt[kNumClasses + 1], s_max, s_bad[3], s_hist[kRLMaxSlots];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * 1024u + tid;
     if (tid <= (uint32_t)kNumClasses) s_cnt[tid] = 0u;
+    if (tid < kRLMaxSlots) s_hist[tid] = 0u;
     if (tid < 3u) s_bad[tid] = 0u;
     if (tid == 0) s_max = 0u;
     __syncthreads();
@@ -975,6 +1240,7 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
                 if (hk > kCtaMaxSmemWords) atomicAdd(&out->huge_keys, hk);
             }
             if (l > kPackedMaxLen) atomicAdd(&s_bad[2], 1u);
+            else if (k < kRLMaxSlots) atomicAdd(&s_hist[k], 1u);
         }
         if (l > kMaxLength) atomicAdd(&s_bad[1], 1u);
     }
@@ -986,6 +1252,7 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
     if (lane == 0 && mk) atomicMax(&s_max, mk);
     __syncthreads();
     if (tid < (uint32_t)kNumClasses && s_cnt[tid]) atomicAdd(&out->class_count[tid], s_cnt[tid]);
+    if (tid < kRLMaxSlots && s_hist[tid]) atomicAdd(&out->k_hist[tid], s_hist[tid]);
     if (tid == 0) {
         if (s_cnt[kNumClasses]) atomicAdd(&out->n_big, s_cnt[kNumClasses]);
         if (s_max) atomicMax(&out->max_k, s_max);
@@ -993,6 +1260,33 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
         if (s_bad[1]) atomicAdd(&out->bad_len, s_bad[1]);
         if (s_bad[2]) atomicAdd(&out->n_wide, s_bad[2]);
     }
+}
+
+// validate_kernel (upload time): 0 <= begin < end <= length for every interval. A warp takes 32 consecutive rows and
+// walks each of them with coalesced loads.
+__global__ void __launch_bounds__(256) validate_kernel(const uint2 *__restrict__ iv, const uint32_t *__restrict__ rowptr,
+                                                       const uint32_t *__restrict__ len, uint32_t n_reads, DevRowStats *out) {
+    const uint32_t lane = lane_id(), warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t bad = 0;
+    for (uint32_t r0 = warp * 32u; r0 < n_reads; r0 += n_warps * 32u) {
+        const uint32_t r = r0 + lane;
+        uint32_t p0 = 0, p1 = 0, l = 0;
+        if (r < n_reads) {
+            p0 = __ldg(rowptr + r);
+            p1 = __ldg(rowptr + r + 1);
+            l = __ldg(len + r);
+        }
+        const uint32_t rows = min(32u, n_reads - r0);
+        for (uint32_t j = 0; j < rows; ++j) {
+            const uint32_t b = __shfl_sync(FULL, p0, j), e = __shfl_sync(FULL, p1, j), lj = __shfl_sync(FULL, l, j);
+            for (uint32_t i = b + lane; i < e; i += 32u) {
+                const uint2 v = __ldg(iv + i);
+                bad += !(v.x < v.y && v.y <= lj);
+            }
+        }
+    }
+    bad = warp_sum(bad);
+    if (lane == 0 && bad) atomicAdd(&out->malformed, bad);
 }
 
 Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, uint64_t big_pairs, size_t *total) {
@@ -1030,6 +1324,21 @@ int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_rea
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+int launch_validate(const uint2 *iv, const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, uint32_t n_iv, DevRowStats *out,
+                    cudaStream_t stream) {
+    if (n_reads == 0 || n_iv == 0) return 0;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    }
+    uint32_t grid = (uint32_t)n_sm * 8u;
+    const uint32_t want = (n_reads + 255u) / 256u;
+    if (grid > want) grid = want;
+    validate_kernel<<<grid, 256, 0, stream>>>(iv, rowptr, len, n_reads, out);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 uint64_t huge_keys_for_row(uint64_t k) {
     const uint64_t p = cta_words(k, true);
     return (k > kSmallMaxK && p > kCtaMaxSmemWords) ? p : 0;
@@ -1046,7 +1355,9 @@ size_t detect_scratch_bytes(uint32_t n_reads, uint32_t n_iv, const RowStats &rs)
 }
 
 int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, cudaStream_t stream) {
-    static int n_sm = 0, occ_sort = 0;
+    static int n_sm = 0, occ_sort = 0, occ_small = 0, occ_mid = 0;
+    constexpr uint32_t kSmallThreads = 32u * YB_RL_WARPS_SMALL, kMidThreads = 32u * YB_RL_WARPS_MID;
+    constexpr size_t kSmallSmem = YB_RL_WARPS_SMALL * rl_warp_smem(kRLSmallSlots), kMidSmem = YB_RL_WARPS_MID * rl_warp_smem(kRLMaxSlots);
     if (!n_sm) {
         int dev = 0, sm = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -1054,7 +1365,11 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         if (cudaFuncSetAttribute(big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCtaMaxSmemWords * sizeof(uint32_t))) != cudaSuccess) return -1;
         if (cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return -1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, sort_kernel, kSortThreads, kSortSmemBytes) != cudaSuccess) return -1;
-        if (occ_sort < 1) return -1;
+        if (cudaFuncSetAttribute(rl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmem) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(rl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMidSmem) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_small, rl_kernel<false>, kSmallThreads, kSmallSmem) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_mid, rl_kernel<true>, kMidThreads, kMidSmem) != cudaSuccess) return -1;
+        if (occ_sort < 1 || occ_small < 1 || occ_mid < 1) return -1;
         n_sm = sm;
     }
     int launches = 0;
@@ -1066,14 +1381,44 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     size_t total = 0;
     Work w = carve(a, a.rows.huge_keys, a.rows.n_big, a.rows.big_pairs, &total);
     if (total > a.scratch_bytes) return -1;
+    // row-per-lane tier: packed rows whose k + min(c, k) + 1 key slots fit 128 leave their lane-group class
+    uint32_t lg_count[kNumClasses];
+    for (int cl = 0; cl < kNumClasses; ++cl) lg_count[cl] = a.rows.class_count[cl];
+    // The row-per-lane tier is opt-in (YB_RL_MAX_SLOTS=64 or 128; read at every launch): measured on B200 it does not
+    // beat the lane-group tier yet, so by default every register-tier row takes the lane-group path.
+    uint32_t rl_max = 0;
+    if (const char *e = getenv("YB_RL_MAX_SLOTS")) {
+        const long v = strtol(e, nullptr, 10);
+        rl_max = v < 0 ? 0u : v > (long)kRLMaxSlots ? kRLMaxSlots : (uint32_t)v;
+    }
+    RLTab rl{};
+    for (uint32_t k = 0; k < kRLMaxSlots; ++k) {
+        const int q = rl_class_of_row(k, 0u, coverage, rl_max);
+        if (q < 0 || !a.rows.k_hist[k]) continue;
+        rl.count[q] += a.rows.k_hist[k];
+        lg_count[class_of_row(k, 0u)] -= a.rows.k_hist[k];
+    }
     // size classes: records grouped by class; batches ordered largest groups first (wide before packed)
     ClassTab tab;
     uint32_t at = 0;
     for (int cl = 0; cl < kNumClasses; ++cl) {
         tab.entry_base[cl] = at;
-        tab.count[cl] = a.rows.class_count[cl];
+        tab.count[cl] = lg_count[cl];
         at += tab.count[cl];
     }
+    for (int q = 0; q < kNumRL; ++q) {
+        rl.entry_base[q] = at;
+        at += rl.count[q];
+    }
+    uint32_t items_small = 0, items_mid = 0;
+    for (int q = 0; q < kNumRL / 2; ++q) {  // q-th class in processing order: N = NMAX - 8 q
+        rl.item_base_small[q] = items_small;
+        items_small += (rl.count[kNumRL / 2 - 1 - q] + 31u) / 32u;
+        rl.item_base_mid[q] = items_mid;
+        items_mid += (rl.count[kNumRL - 1 - q] + 31u) / 32u;
+    }
+    rl.item_base_small[kNumRL / 2] = items_small;
+    rl.item_base_mid[kNumRL / 2] = items_mid;
     uint32_t items = 0;
     int q = 0;
     for (int gi = kNumG - 1; gi >= 0; --gi) {
@@ -1091,7 +1436,7 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     }
     tab.item_base[kNumClasses] = items;
 
-    scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, tab);
+    scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, tab, rl, coverage, rl_max);
     ++launches;
     if (a.rows.n_big) {
         // shared memory for the largest row (wide if any read is); rows beyond kCtaMaxSmemWords sort in a global slab
@@ -1110,6 +1455,20 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         const uint32_t want = (items + kSortWarps - 1u) / kSortWarps;
         if (grid > want) grid = want;
         sort_kernel<<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage);
+        ++launches;
+    }
+    if (items_mid) {
+        uint32_t grid = (uint32_t)(n_sm * occ_mid);
+        const uint32_t want = (items_mid + YB_RL_WARPS_MID - 1u) / YB_RL_WARPS_MID;
+        if (grid > want) grid = want;
+        rl_kernel<true><<<grid, kMidThreads, kMidSmem, stream>>>(a, w, rl, coverage);
+        ++launches;
+    }
+    if (items_small) {
+        uint32_t grid = (uint32_t)(n_sm * occ_small);
+        const uint32_t want = (items_small + YB_RL_WARPS_SMALL - 1u) / YB_RL_WARPS_SMALL;
+        if (grid > want) grid = want;
+        rl_kernel<false><<<grid, kSmallThreads, kSmallSmem, stream>>>(a, w, rl, coverage);
         ++launches;
     }
     scan_parts_kernel<<<1, 1024, 0, stream>>>(a, w);

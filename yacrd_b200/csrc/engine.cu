@@ -720,9 +720,15 @@ int yb_upload(yb_ctx *c) {
         rs.huge_keys = ds.huge_keys;
         rs.n_wide = ds.n_wide;
         for (int q = 0; q < yb::kNumClasses; ++q) rs.class_count[q] = ds.class_count[q];
+        for (uint32_t q = 0; q < yb::kRLMaxSlots; ++q) rs.k_hist[q] = ds.k_hist[q];
         c->rows = rs;
         c->max_k = ds.max_k;
     }
+    // 0 <= begin < end <= length is tested once, here, behind the interval copy (the CSR cannot change afterwards);
+    // yb_download reads the count back with the results
+    const int vl = yb::launch_validate(c->d_iv.p, c->d_rowptr.p, c->d_len.p, c->n_reads, c->n_iv, c->d_rowstats.p, c->stream);
+    if (vl < 0) return c->cuda_fail(cudaGetLastError(), "interval validation kernel");
+    c->stats.kernel_launches += (uint64_t)vl;
     const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->rows);
     if (!c->d_scratch.reserve(sb)) return c->fail(YB_ERR_NOMEM, "device scratch allocation failed (%zu bytes)", sb);
     c->stats.h2d_bytes += sizeof(uint32_t) * (2 * n + 1) + sizeof(uint2) * m;
@@ -801,6 +807,8 @@ int yb_download(yb_ctx *c) {
         return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
     YB_CUDA(c, cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, sizeof(uint32_t) * yb::kNumCounters, cudaMemcpyDeviceToHost, c->stream));
     YB_CUDA(c, cudaMemcpyAsync(c->h_gap_ptr.p, c->d_gap_ptr.p, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, c->stream));
+    if (!c->from_report)
+        YB_CUDA(c, cudaMemcpyAsync(c->h_rowstats.p, c->d_rowstats.p, sizeof(yb::DevRowStats), cudaMemcpyDeviceToHost, c->stream));
     if (n) {
         YB_CUDA(c, cudaMemcpyAsync(c->h_cls.p, c->d_cls.p, n, cudaMemcpyDeviceToHost, c->stream));
         const uint8_t *bm = c->n_peers && !c->from_report ? c->peer_gather[c->peer_rank] + (size_t)c->peer_rank * c->peer_slot_bytes
@@ -808,10 +816,9 @@ int yb_download(yb_ctx *c) {
         YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p, bm, c->bitmap_bytes(), cudaMemcpyDeviceToHost, c->stream));
     }
     YB_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->h_counters.p[yb::kCntMalformed])
+    if (const uint32_t bad = c->from_report ? 0u : c->h_rowstats.p->malformed)
         return c->fail(YB_ERR_MALFORMED_INTERVAL,
-                       "%u interval(s) violate 0 <= begin < end <= length; the reference's result is undefined for them",
-                       c->h_counters.p[yb::kCntMalformed]);
+                       "%u interval(s) violate 0 <= begin < end <= length; the reference's result is undefined for them", bad);
     if (c->h_counters.p[yb::kCntPeerTimeout])
         return c->fail(YB_ERR_STATE, "peer all-gather: %u rank(s) never signalled this step", c->h_counters.p[yb::kCntPeerTimeout]);
     if (c->h_counters.p[yb::kCntStageOverflow])

@@ -22,15 +22,15 @@ enum Counter : uint32_t {
     kCntBigBump = 7,     // bump allocator (in pairs) of the big tier's side buffer
     kCntTierWarp = 8,    // reads taken by each tier
     kCntTierCta = 9,
-    kCntTierHuge = 10,
     kCntStage = 11,      // bump allocator (in pairs) of the bad-region staging buffer
-    kCntTileSlow = 12,   // dynamic tile scheduler of the generic (u32) pass
+    kCntTileSmall = 12,  // dynamic batch scheduler of the row-per-lane tier, rows of <= 64 slots
+    kCntTileMid = 10,    // the same for rows of 72 .. 128 slots
     kCntStageOverflow = 14,  // rows whose bad regions did not fit the staging buffer (must stay 0)
     kCntPeerTimeout = 15,  // the peer barrier gave up waiting (a rank died or never launched)
     kCntTicket = 13,     // order_kernel: dynamic part index (decoupled look-back needs in-order starts)
-    kCntClassCursor = 16,  // kNumClasses cursors of the worklist scatter
-    kCntHist = 48,         // kHistSlots x {NotBad, Chimeric, NotCovered}: the detect step's class histogram, striped
-    kNumCounters = 48 + 3 * 32
+    kCntClassCursor = 16,  // kNumClasses + kNumRL cursors of the worklist scatter
+    kCntHist = 64,         // kHistSlots x {NotBad, Chimeric, NotCovered}: the detect step's class histogram, striped
+    kNumCounters = 64 + 3 * 32
 };
 constexpr uint32_t kHistSlots = 32;
 
@@ -48,6 +48,21 @@ __host__ __device__ inline uint32_t class_lanes(int gi) {
 constexpr uint32_t kPackedMaxLen = 65534u;
 constexpr uint32_t kRegisterTierMaxK = 512u;
 
+// Row-per-lane tier: a packed row with k intervals at threshold c takes s = k + min(c, k) + 1 key slots (its
+// intervals plus min(c, k) + 1 sentinel ends, see detect.cu); rows with s <= kRLMaxSlots are sorted by ONE lane in
+// registers, 32 rows of one slot class per warp. Slot classes N = 8, 16, ..., 128.
+constexpr int kNumRL = 16;
+constexpr uint32_t kRLMaxSlots = 128u;
+constexpr uint32_t kRLSmallSlots = 64u;  // classes up to here run in the low-register kernel
+constexpr int kNumAllClasses = kNumClasses + kNumRL;
+// Slot class (0 .. kNumRL-1) of a row in the row-per-lane tier, or -1 if the row does not belong there.
+// max_slots (<= kRLMaxSlots) is where the tier ends: a tuning knob (YB_RL_MAX_SLOTS), 0 switches the tier off.
+__host__ __device__ inline int rl_class_of_row(uint32_t k, uint32_t len, uint32_t c, uint32_t max_slots = kRLMaxSlots) {
+    if (len > kPackedMaxLen || k >= max_slots) return -1;
+    const uint32_t s = k + (c < k ? c : k) + 1u;
+    return s <= max_slots ? (int)((s + 7u) / 8u) - 1 : -1;
+}
+
 // Size class of a row, or -1 for a big row (k > 512).
 __host__ __device__ inline int class_of_row(uint32_t k, uint32_t len) {
     if (k > kRegisterTierMaxK) return -1;
@@ -62,6 +77,7 @@ struct RowStats {
     uint64_t huge_keys = 0;  // sum over rows beyond the shared-memory tier of next_pow2(2k)
     uint64_t n_wide = 0;     // rows longer than kPackedMaxLen (positions do not fit 16 bits)
     uint32_t class_count[kNumClasses] = {};  // rows per size class (k <= 512)
+    uint32_t k_hist[kRLMaxSlots] = {};       // packed rows (len <= kPackedMaxLen) with exactly k < 128 intervals
 };
 
 
@@ -98,9 +114,18 @@ struct DevRowStats {
     uint32_t pad_;
     unsigned long long big_pairs;  // sum over big rows of k + 1
     unsigned long long huge_keys;  // sum over rows beyond the shared-memory tier of next_pow2(2k)
+    uint32_t k_hist[kRLMaxSlots];  // packed rows with exactly k < 128 intervals
+    uint32_t malformed;            // intervals violating 0 <= begin < end <= length (launch_validate)
+    uint32_t pad2_[3];
 };
 // Zeroes *out and fills it from the device-resident rowptr / len (one kernel on `stream`). Returns launches or -1.
 int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream);
+
+// Counts the intervals violating 0 <= begin < end <= length into out->malformed (one streaming kernel on `stream`,
+// after launch_row_stats which zeroes *out). The CSR is immutable once uploaded, so this runs once per upload and the
+// row-per-lane kernels do not repeat the test at every detect step. Returns launches or -1.
+int launch_validate(const uint2 *iv, const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, uint32_t n_iv,
+                    DevRowStats *out, cudaStream_t stream);
 
 // Bytes of scratch launch_detect needs for a CSR of this shape.
 size_t detect_scratch_bytes(uint32_t n_reads, uint32_t n_iv, const RowStats &rs);
