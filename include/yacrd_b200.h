@@ -150,6 +150,14 @@ const uint8_t *yb_class_bitmap(yb_ctx *ctx, size_t *n_bytes);
 /* The whole result as a CSR of bad regions: gap_ptr[0..n_reads] and (begin,end) pairs. Host views. */
 const uint32_t *yb_gap_ptr(yb_ctx *ctx, size_t *n);
 const uint32_t *yb_gaps(yb_ctx *ctx, size_t *n_pairs);
+/* The post-detection editors (main.rs:87-117) over the computed results: editor::scrubbing (editor/scrubbing.rs:34),
+ * editor::filter (editor/filter.rs:34), editor::extract (editor/extract.rs:34), editor::split (editor/split.rs:34).
+ * input_path: fasta / fastq (all four) or paf / m4 (filter and extract only), type by util.rs:39-55; the output keeps
+ * the input's format. Needs yb_compute_all_bad_part first (the class of a read is the one computed with that call's
+ * not_coverage, which is what main.rs passes to the editors too). Errors mirror error.rs: CantRunOperationOnFile ->
+ * YB_ERR_WRONG_FORMAT, UnableToDetectFileFormat -> YB_ERR_UNKNOWN_FORMAT, ReadingError -> YB_ERR_READING. */
+typedef enum yb_editor { YB_EDIT_SCRUBB = 0, YB_EDIT_FILTER = 1, YB_EDIT_EXTRACT = 2, YB_EDIT_SPLIT = 3 } yb_editor;
+int yb_edit(yb_ctx *ctx, int editor, const char *input_path, const char *output_path);
 /* FromReport::new, stack.rs:182-215: load an existing .yacrd report instead of computing. */
 int yb_init_report(yb_ctx *ctx, const char *path);
 int yb_init_report_buffer(yb_ctx *ctx, const char *text, size_t n_bytes);

@@ -18,8 +18,16 @@ Outputs (committed):
                            ORACLE-DERIVED (not reference goldens): the pinned oracle's report for the
                            README presets the reference never pins (-c 4 -n 0.4, -c 3 -n 0.4,
                            -c 1 -n 0.8). Regression vectors for the oracle itself.
+  c1_reads.fastq.gz        tests/reads.fastq (461 reads), gzip -9 with a zero timestamp: the editors' input
+  c1_editors.json          sha256 / byte count / record count of tests/truth.{filter,extract,split,scrubb}.fastq
+                           (tests/run.rs:163-300 pins the editors' output byte for byte, in input order)
+  c1_truth.extract.fastq   the smallest of the four, in full (a readable diff when a digest does not match)
 """
+import gzip
+import hashlib
+import json
 import os
+import shutil
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -53,6 +61,22 @@ def main():
             fh.write("\n".join(lines) + "\n")
         cnt = {t: sum(l.startswith(t + "\t") for l in lines) for t in o.TYPE_NAMES}
         print("c=%d n=%s -> %s" % (c, n, cnt))
+    from oracle import editors_oracle as eo
+    raw = open(os.path.join(REF, "reads.fastq"), "rb").read()
+    with open(os.path.join(HERE, "c1_reads.fastq.gz"), "wb") as fh:
+        with gzip.GzipFile(filename="", mode="wb", compresslevel=9, fileobj=fh, mtime=0) as gz:
+            gz.write(raw)
+    look = eo.report_lookup(open(os.path.join(REF, "truth.yacrd")).read())
+    digests = {}
+    for op, name in ((eo.FILTER, "filter"), (eo.EXTRACT, "extract"), (eo.SPLIT, "split"), (eo.SCRUBB, "scrubb")):
+        want = open(os.path.join(REF, "truth.%s.fastq" % name), "rb").read()
+        assert eo.fastq(op, raw, look, 0.8) == want, "editors oracle does not reproduce truth.%s.fastq" % name
+        digests[name] = {"sha256": hashlib.sha256(want).hexdigest(), "bytes": len(want), "records": want.count(b"\n") // 4}
+    digests["input"] = {"sha256": hashlib.sha256(raw).hexdigest(), "bytes": len(raw), "records": raw.count(b"\n") // 4}
+    with open(os.path.join(HERE, "c1_editors.json"), "w") as fh:
+        json.dump(digests, fh, indent=1, sort_keys=True)
+        fh.write("\n")
+    shutil.copyfile(os.path.join(REF, "truth.extract.fastq"), os.path.join(HERE, "c1_truth.extract.fastq"))
     print("golden fixtures written to", HERE)
 
 

@@ -31,8 +31,10 @@ def test_cli_version_help_and_argument_errors():
     assert r.returncode == 2 and "--output" in r.stderr
     r = run("-i", "x.paf", "-o", "y", "-c", "abc")
     assert r.returncode == 2
-    r = run("-i", "x.paf", "-o", "y", "scrubb", "-i", "a.fq", "-o", "b.fq")
-    assert r.returncode == 2 and "not part of this build" in r.stderr
+    r = run("-i", "x.paf", "-o", "y", "scrubb", "-i", "a.fq")  # cli.rs:94-103: both are required
+    assert r.returncode == 2 and "--output" in r.stderr
+    r = run("-i", "x.paf", "-o", "y", "filter", "-i", "a.fq", "-o", "b.fq", "--bogus")
+    assert r.returncode == 2
 
 
 @pytest.mark.gpu

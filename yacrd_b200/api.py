@@ -359,3 +359,30 @@ class FromReport(_BadPart):
 
     def compute_all_bad_part(self):  # stack.rs:245 (no pile-up); classification runs on the device
         self.ctx.compute_all(0, self.not_coverage)
+
+
+# ---- editors (reference src/editor/{scrubbing,filter,extract,split}.rs): same names and argument order ----------
+def _edit(op, input_path, output_path, badregions, not_covered, buffer_size):
+    """The class of a read was computed on the device with the BadPart's own not_coverage; the reference passes the
+    same value to its editors (main.rs:87-117), so a different one here is an error, not a silent re-classification."""
+    if float(not_covered) != float(badregions.not_coverage):
+        raise ValueError("editors use the not_coverage the bad parts were classified with (%r), got %r"
+                         % (badregions.not_coverage, not_covered))
+    c = badregions.ctx
+    c._ck(c._L.yb_edit(c._h, op, _b(input_path), _b(output_path)))
+
+
+def scrubbing(input_path, output_path, badregions, not_covered, buffer_size=8192):  # editor/scrubbing.rs:34-71
+    _edit(N.EDIT_SCRUBB, input_path, output_path, badregions, not_covered, buffer_size)
+
+
+def filter(input_path, output_path, badregions, not_covered, buffer_size=8192):  # editor/filter.rs:34-63
+    _edit(N.EDIT_FILTER, input_path, output_path, badregions, not_covered, buffer_size)
+
+
+def extract(input_path, output_path, badregions, not_covered, buffer_size=8192):  # editor/extract.rs:34-63
+    _edit(N.EDIT_EXTRACT, input_path, output_path, badregions, not_covered, buffer_size)
+
+
+def split(input_path, output_path, badregions, not_covered, buffer_size=8192):  # editor/split.rs:34-71
+    _edit(N.EDIT_SPLIT, input_path, output_path, badregions, not_covered, buffer_size)

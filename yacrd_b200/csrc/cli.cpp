@@ -4,9 +4,9 @@
 //
 // Same flags, defaults and version string as the reference; the work goes through the C ABI (include/yacrd_b200.h)
 // exactly as main.rs drives its trait objects: init (main.rs:57) -> compute_all_bad_part (main.rs:78) -> one report
-// line per read (main.rs:80-84). The post-detection editors (scrubb / filter / extract / split, main.rs:87-117) are
-// outside this build's scope and are refused, not emulated. `-d/--ondisk` is accepted for
-// compatibility: the device path keeps the batch resident, so the on-disk store is not used.
+// line per read (main.rs:80-84) -> the optional editor subcommand (main.rs:87-117):
+//   yacrd-b200 -i overlaps.paf -o report.yacrd scrubb|filter|extract|split -i reads.fastq -o edited.fastq
+// `-d/--ondisk` is accepted for compatibility: the device path keeps the batch resident, so the on-disk store is not used.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,7 +35,11 @@ void usage(FILE *f) {
             "        --device <N>                    CUDA device ordinal [default: current]\n"
             "        --timing                        phase times on stderr\n"
             "    -h, --help    -V, --version\n\n"
-            "SUBCOMMANDS scrubb | filter | extract | split are not part of this build.\n",
+            "SUBCOMMANDS (after the options above):\n"
+            "    scrubb  -i <INPUT> -o <OUTPUT>   all bad regions of the reads are removed (fasta|fastq)\n"
+            "    filter  -i <INPUT> -o <OUTPUT>   records marked Chimeric or NotCovered are dropped (fasta|fastq|paf|m4)\n"
+            "    extract -i <INPUT> -o <OUTPUT>   only those records are kept (fasta|fastq|paf|m4)\n"
+            "    split   -i <INPUT> -o <OUTPUT>   Chimeric reads are cut at their interior bad regions (fasta|fastq)\n",
             yb_version());
 }
 
@@ -54,7 +58,8 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 }  // namespace
 
 int main(int argc, char **argv) {
-    std::string input, output;
+    std::string input, output, sub_input, sub_output;
+    int subcmd = -1;  // yb_editor
     uint64_t coverage = 0, threads = 0, buffer_size = 8192, dummy;
     double not_coverage = 0.8;
     int device = -1;
@@ -110,9 +115,22 @@ int main(int argc, char **argv) {
             device = atoi(value("--device"));
         } else if (a == "--timing") {
             timing = true;
-        } else if (a == "scrubb" || a == "filter" || a == "extract" || a == "split") {
-            fprintf(stderr, "error: the '%s' editor is not part of this build (detect path only); run the reference's editor on the report\n", a.c_str());
-            return 2;
+        } else if (a == "scrubb" || a == "filter" || a == "extract" || a == "split") {  // cli.rs:77-137: the rest belongs to it
+            subcmd = a == "scrubb" ? YB_EDIT_SCRUBB : a == "filter" ? YB_EDIT_FILTER : a == "extract" ? YB_EDIT_EXTRACT : YB_EDIT_SPLIT;
+            for (++i; i < argc; ++i) {
+                const std::string b = argv[i];
+                if (b == "-i" || b == "--input") sub_input = value("--input");
+                else if (b == "-o" || b == "--output") sub_output = value("--output");
+                else {
+                    fprintf(stderr, "error: Found argument '%s' which wasn't expected, or isn't valid in this context\n", b.c_str());
+                    return 2;
+                }
+            }
+            if (sub_input.empty() || sub_output.empty()) {
+                fprintf(stderr, "error: The following required arguments were not provided:%s%s\n", sub_input.empty() ? "\n    --input <INPUT>" : "",
+                        sub_output.empty() ? "\n    --output <OUTPUT>" : "");
+                return 2;
+            }
         } else {
             fprintf(stderr, "error: Found argument '%s' which wasn't expected, or isn't valid in this context\n", a.c_str());
             return 2;
@@ -146,6 +164,7 @@ int main(int argc, char **argv) {
     if (yb_compute_all_bad_part(ctx, coverage, not_coverage) != YB_OK) return fail("computing the bad regions");
     const double t3 = now_s();
     if (yb_write_report(ctx, output.c_str()) != YB_OK) return fail("writing the report");
+    if (subcmd >= 0 && yb_edit(ctx, subcmd, sub_input.c_str(), sub_output.c_str()) != YB_OK) return fail("running the editor");
     const double t4 = now_s();
     if (timing) {
         yb_stats st;

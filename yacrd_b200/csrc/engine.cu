@@ -983,6 +983,15 @@ int yb_get_bad_part(yb_ctx *c, const char *id, size_t id_len, const uint32_t **g
     return yb_get_bad_part_at(c, (uint32_t)i, gap_pairs, n_gaps, length, cls);
 }
 
+int yb_edit(yb_ctx *c, int editor, const char *input_path, const char *output_path) {
+    if (!c || !input_path || !output_path) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->downloaded) return c->fail(YB_ERR_STATE, "editors need the results: call yb_compute_all_bad_part first");
+    std::string msg;
+    const int rc = yb::run_editor(c, editor, input_path, output_path, c->read_buffer_size, &msg);
+    if (rc != YB_OK && !msg.empty()) return c->fail(rc, "%s", msg.c_str());
+    return rc;
+}
+
 const uint8_t *yb_classes(yb_ctx *c, size_t *n) {
     if (!c || !c->downloaded) return nullptr;
     if (n) *n = c->n_reads;

@@ -145,4 +145,8 @@ typedef bool (*CsrAllocFn)(void *sink, size_t n_reads, size_t n_iv, uint32_t **r
 bool ingest_buffer_parallel(const char *text, size_t n, int format, int threads, CsrAllocFn alloc, void *sink, BulkIds *ids,
                             IngestError *err);
 
+// editors.cpp: runs one post-detection editor (yb_editor) over input_path -> output_path, asking `ctx` for the
+// results through the public ABI. Returns a yb_status; *error gets the message unless the context already has it.
+int run_editor(struct ::yb_ctx *ctx, int op, const char *input_path, const char *output_path, size_t buffer_size, std::string *error);
+
 }  // namespace yb
