@@ -10,11 +10,13 @@
 // first space and written back with one space; fasta sequences are re-wrapped at 80 columns; fasta records cut by
 // scrubb / split lose their description, fastq records keep it (scrubbing.rs:139-153 vs 211-224).
 // Overlap files (filter / extract only) pass through line by line; csv quoting is not interpreted.
-// Compressed input (util.rs:57-87, niffler) is outside this build: gzip / bzip2 / xz magic is refused.
+// Compression (util.rs:57-87, niffler): gzip input is read through zlib and the output is gzip again (level 1, as
+// util.rs:84 asks); bzip2 / xz are refused (no development headers in this image).
 #include <errno.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <zlib.h>
 
 #include <string>
 #include <vector>
@@ -43,14 +45,14 @@ struct Err {
 // Buffered line reader: lines end with '\n' (a preceding '\r' is dropped); the last line may lack the terminator.
 class LineReader {
   public:
-    LineReader(FILE *f, size_t cap) : f_(f), buf_(cap < (1u << 16) ? (1u << 16) : cap) {}
+    LineReader(gzFile f, size_t cap) : f_(f), buf_(cap < (1u << 16) ? (1u << 16) : cap) {}
     // false at end of input. *line stays valid until the next call.
     bool next(std::string *line) {
         line->clear();
         bool any = false;
         for (;;) {
             if (pos_ == end_) {
-                end_ = fread(buf_.data(), 1, buf_.size(), f_);
+                end_ = fill();
                 pos_ = 0;
                 if (end_ == 0) break;
             }
@@ -69,11 +71,11 @@ class LineReader {
         if (any && !line->empty() && line->back() == '\r') line->pop_back();
         return any;
     }
-    bool io_error() const { return ferror(f_) != 0; }
+    bool io_error() const { return bad_; }
     // first bytes of the stream without consuming them (compression sniffing); call before next()
     size_t peek(unsigned char *out, size_t n) {
         if (pos_ == end_) {
-            end_ = fread(buf_.data(), 1, buf_.size(), f_);
+            end_ = fill();
             pos_ = 0;
         }
         const size_t m = end_ - pos_ < n ? end_ - pos_ : n;
@@ -82,18 +84,24 @@ class LineReader {
     }
 
   private:
-    FILE *f_;
+    size_t fill() {  // zlib reads plain files as they are and inflates gzip ones
+        const int got = gzread(f_, buf_.data(), (unsigned)buf_.size());
+        if (got < 0) bad_ = true;
+        return got > 0 ? (size_t)got : 0;
+    }
+    gzFile f_;
     std::vector<char> buf_;
     size_t pos_ = 0, end_ = 0;
+    bool bad_ = false;
 };
 
 class Out {
   public:
-    Out(FILE *f, size_t cap) : f_(f), buf_(cap < (1u << 16) ? (1u << 16) : cap) {}
+    Out(FILE *f, gzFile g, size_t cap) : f_(f), g_(g), buf_(cap < (1u << 16) ? (1u << 16) : cap) {}
     void put(const char *p, size_t n) {
         if (n > buf_.size() - len_) flush();
         if (n > buf_.size()) {
-            ok_ = ok_ && fwrite(p, 1, n, f_) == n;
+            ok_ = ok_ && write(p, n);
             return;
         }
         memcpy(buf_.data() + len_, p, n);
@@ -102,13 +110,25 @@ class Out {
     void put(const std::string &s) { put(s.data(), s.size()); }
     void put(char ch) { put(&ch, 1); }
     void flush() {
-        if (len_) ok_ = ok_ && fwrite(buf_.data(), 1, len_, f_) == len_;
+        if (len_) ok_ = ok_ && write(buf_.data(), len_);
         len_ = 0;
     }
     bool ok() const { return ok_; }
 
   private:
+    bool write(const char *p, size_t n) {
+        if (g_) {
+            for (size_t at = 0; at < n;) {
+                const unsigned part = n - at > (1u << 30) ? (1u << 30) : (unsigned)(n - at);
+                if (gzwrite(g_, p + at, part) != (int)part) return false;
+                at += part;
+            }
+            return true;
+        }
+        return fwrite(p, 1, n, f_) == n;
+    }
     FILE *f_;
+    gzFile g_;
     std::vector<char> buf_;
     size_t len_ = 0;
     bool ok_ = true;
@@ -348,30 +368,34 @@ int run_editor(yb_ctx *ctx, int op, const char *input_path, const char *output_p
     if (t == 'y' || ((t == 'p' || t == 'm') && (op == YB_EDIT_SCRUBB || op == YB_EDIT_SPLIT)))
         return done(err.set(YB_ERR_WRONG_FORMAT, "Can't run %s on %s file %s", kOpName[op], t == 'y' ? "yacrd" : (t == 'p' ? "paf" : "m4"),
                             input_path));
-    FILE *fi = fopen(input_path, "rb");
+    gzFile fi = gzopen(input_path, "rb");
     if (!fi) return done(err.set(YB_ERR_CANT_READ_FILE, "Can't open file %s: %s", input_path, strerror(errno)));
+    gzbuffer(fi, 1u << 18);
     LineReader in(fi, buffer_size);
     unsigned char magic[6] = {0};
     const size_t got = in.peek(magic, sizeof magic);
-    if ((got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) || (got >= 3 && !memcmp(magic, "BZh", 3)) ||
-        (got >= 6 && !memcmp(magic, "\xfd" "7zXZ\0", 6))) {
-        fclose(fi);
-        return done(err.set(YB_ERR_CANT_READ_FILE, "%s is compressed; decompress it first (compressed input is out of scope)", input_path));
+    const bool gz = gzdirect(fi) == 0;  // niffler sniffs the magic number; the output keeps the input's compression
+    if (!gz && ((got >= 3 && !memcmp(magic, "BZh", 3)) || (got >= 6 && !memcmp(magic, "\xfd" "7zXZ\0", 6)))) {
+        gzclose(fi);
+        return done(err.set(YB_ERR_CANT_READ_FILE, "%s is bzip2- or xz-compressed; only gzip is read by this build", input_path));
     }
-    FILE *fo = fopen(output_path, "wb");
-    if (!fo) {
-        fclose(fi);
+    FILE *fo = nullptr;
+    gzFile go = nullptr;
+    if (gz) go = gzopen(output_path, "wb1");  // util.rs:84: niffler::compression::Level::One
+    else fo = fopen(output_path, "wb");
+    if (!fo && !go) {
+        gzclose(fi);
         return done(err.set(YB_ERR_CANT_WRITE_FILE, "Can't create file %s: %s", output_path, strerror(errno)));
     }
-    Out out(fo, buffer_size);
+    Out out(fo, go, buffer_size);
     Lookup look{ctx};
     int rc;
     if (t == 'a') rc = edit_fasta(op, in, out, look, &err);
     else if (t == 'q') rc = edit_fastq(op, in, out, look, &err);
     else rc = edit_overlaps(op, t == 'p' ? '\t' : ' ', t == 'p' ? 5 : 1, in, out, look, &err);
     out.flush();
-    fclose(fi);
-    const bool wrote = out.ok() && fclose(fo) == 0;
+    gzclose(fi);
+    const bool wrote = (go ? gzclose(go) == Z_OK : fclose(fo) == 0) && out.ok();
     if (rc == YB_OK && !wrote) rc = err.set(YB_ERR_WRITING, "Writing of the file %s failed", output_path);
     if (rc != YB_OK && err.msg.empty()) return rc;  // the context already holds the message (yb_get_bad_part)
     return done(rc);
