@@ -46,7 +46,7 @@ def main():
     print("c = %d" % c)
     print("%9s %9s %11s %9s %10s %12s" % ("k range", "rows", "intervals", "us/step", "ns/row", "ps/interval"))
     for lo, hi in ranges:
-        csr = subset(base, lo, hi, 24e6)
+        csr = subset(base, lo, hi, float(os.environ.get("SWEEP_INTERVALS", "24e6")))
         if csr is None:
             continue
         fm = yb.FullMemory(device=0)

@@ -456,7 +456,7 @@ __device__ void cta_row(const DetectArgs &a, const Work &w, uint32_t *keys, uint
 __global__ void __launch_bounds__(kCtaThreads) big_kernel(DetectArgs a, Work w, uint32_t c, uint32_t smem_words) {
     extern __shared__ __align__(16) uint32_t cta_smem[];
     __shared__ uint32_t sh[16];
-    const uint32_t n_big = a.counters[kCntBigList];
+    const uint32_t n_big = (uint32_t)a.rows.n_big;  // the host knows it from the row statistics
     for (uint32_t j = blockIdx.x; j < n_big; j += gridDim.x) {
         const uint32_t r = w.big_list[j];
         const uint32_t k = a.rowptr[r + 1] - a.rowptr[r];
@@ -1025,6 +1025,14 @@ __global__ void __launch_bounds__(32 * (MID ? YB_RL_WARPS_MID : YB_RL_WARPS_SMAL
         return rec;
     };
     uint32_t item = blockIdx.x * (blockDim.x >> 5) + wid;
+#ifdef YB_RL_SKEW_NS
+    {   // the warps of a scheduler would otherwise walk through the same phases at the same time (same class, same cost,
+        // same start): all loading, then all sorting. One start-up delay per resident CTA slot takes them out of step.
+        const uint32_t per_slot = max(1u, gridDim.x / (MID ? YB_RL_MIN_CTAS_MID : YB_RL_MIN_CTAS_SMALL));
+        const uint32_t slot = blockIdx.x / per_slot;
+        if (slot) __nanosleep(slot * YB_RL_SKEW_NS);
+    }
+#endif
     uint32_t n0, n1, n2;
     uint4 rec0 = load_rec(item, n0);
     uint4 rec1 = load_rec(item + n_warps, n1);
@@ -1315,7 +1323,79 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, uint64_t big
     return w;
 }
 
+// The step's class tables: where every class's records sit in the worklist and how its batches are numbered.
+struct Plan {
+    ClassTab tab;
+    RLTab rl;
+    uint32_t rl_max, items, items_small, items_mid;
+};
+Plan make_plan(const DetectArgs &a, uint32_t coverage, uint32_t rl_max) {
+    Plan pl{};
+    ClassTab &tab = pl.tab;
+    RLTab &rl = pl.rl;
+    pl.rl_max = rl_max;
+    // row-per-lane tier: packed rows whose k + min(c, k) + 1 key slots fit 128 leave their lane-group class
+    uint32_t lg_count[kNumClasses];
+    for (int cl = 0; cl < kNumClasses; ++cl) lg_count[cl] = a.rows.class_count[cl];
+    for (uint32_t k = 0; k < kRLMaxSlots; ++k) {
+        const int q = rl_class_of_row(k, 0u, coverage, rl_max);
+        if (q < 0 || !a.rows.k_hist[k]) continue;
+        rl.count[q] += a.rows.k_hist[k];
+        lg_count[class_of_row(k, 0u)] -= a.rows.k_hist[k];
+    }
+    // size classes: records grouped by class; batches ordered largest groups first (wide before packed)
+    uint32_t at = 0;
+    for (int cl = 0; cl < kNumClasses; ++cl) {
+        tab.entry_base[cl] = at;
+        tab.count[cl] = lg_count[cl];
+        at += tab.count[cl];
+    }
+    for (int q = 0; q < kNumRL; ++q) {
+        rl.entry_base[q] = at;
+        at += rl.count[q];
+    }
+    uint32_t items_small = 0, items_mid = 0;
+    for (int q = 0; q < kNumRL / 2; ++q) {  // q-th class in processing order: N = NMAX - 8 q
+        rl.item_base_small[q] = items_small;
+        items_small += (rl.count[kNumRL / 2 - 1 - q] + 31u) / 32u;
+        rl.item_base_mid[q] = items_mid;
+        items_mid += (rl.count[kNumRL - 1 - q] + 31u) / 32u;
+    }
+    rl.item_base_small[kNumRL / 2] = items_small;
+    rl.item_base_mid[kNumRL / 2] = items_mid;
+    uint32_t items = 0;
+    int q = 0;
+    for (int gi = kNumG - 1; gi >= 0; --gi) {
+        for (int wide = 1; wide >= 0; --wide) {
+            const int cl = gi + (wide ? kNumG : 0);
+            const uint32_t G = class_lanes(gi), rpb = 32u / G;
+            tab.lanes[cl] = G;
+            tab.rpb[cl] = rpb;
+            tab.inv[cl] = (65536u + G - 1u) / G;
+            tab.order[q] = (uint32_t)cl;
+            tab.item_base[q] = items;
+            items += (tab.count[cl] + rpb - 1u) / rpb;
+            ++q;
+        }
+    }
+    tab.item_base[kNumClasses] = items;
+    pl.items = items;
+    pl.items_small = items_small;
+    pl.items_mid = items_mid;
+    return pl;
+}
+
 }  // namespace
+
+// The row-per-lane tier is opt-in (YB_RL_MAX_SLOTS=64 or 128; read at every launch): measured on B200 it does not
+// beat the lane-group tier yet, so by default every register-tier row takes the lane-group path.
+uint32_t rl_max_slots() {
+    if (const char *e = getenv("YB_RL_MAX_SLOTS")) {
+        const long v = strtol(e, nullptr, 10);
+        return v < 0 ? 0u : v > (long)kRLMaxSlots ? kRLMaxSlots : (uint32_t)v;
+    }
+    return 0u;
+}
 
 int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream) {
     if (cudaMemsetAsync(out, 0, sizeof(DevRowStats), stream) != cudaSuccess) return -1;
@@ -1381,63 +1461,18 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     size_t total = 0;
     Work w = carve(a, a.rows.huge_keys, a.rows.n_big, a.rows.big_pairs, &total);
     if (total > a.scratch_bytes) return -1;
-    // row-per-lane tier: packed rows whose k + min(c, k) + 1 key slots fit 128 leave their lane-group class
-    uint32_t lg_count[kNumClasses];
-    for (int cl = 0; cl < kNumClasses; ++cl) lg_count[cl] = a.rows.class_count[cl];
-    // The row-per-lane tier is opt-in (YB_RL_MAX_SLOTS=64 or 128; read at every launch): measured on B200 it does not
-    // beat the lane-group tier yet, so by default every register-tier row takes the lane-group path.
-    uint32_t rl_max = 0;
-    if (const char *e = getenv("YB_RL_MAX_SLOTS")) {
-        const long v = strtol(e, nullptr, 10);
-        rl_max = v < 0 ? 0u : v > (long)kRLMaxSlots ? kRLMaxSlots : (uint32_t)v;
-    }
-    RLTab rl{};
-    for (uint32_t k = 0; k < kRLMaxSlots; ++k) {
-        const int q = rl_class_of_row(k, 0u, coverage, rl_max);
-        if (q < 0 || !a.rows.k_hist[k]) continue;
-        rl.count[q] += a.rows.k_hist[k];
-        lg_count[class_of_row(k, 0u)] -= a.rows.k_hist[k];
-    }
-    // size classes: records grouped by class; batches ordered largest groups first (wide before packed)
-    ClassTab tab;
-    uint32_t at = 0;
-    for (int cl = 0; cl < kNumClasses; ++cl) {
-        tab.entry_base[cl] = at;
-        tab.count[cl] = lg_count[cl];
-        at += tab.count[cl];
-    }
-    for (int q = 0; q < kNumRL; ++q) {
-        rl.entry_base[q] = at;
-        at += rl.count[q];
-    }
-    uint32_t items_small = 0, items_mid = 0;
-    for (int q = 0; q < kNumRL / 2; ++q) {  // q-th class in processing order: N = NMAX - 8 q
-        rl.item_base_small[q] = items_small;
-        items_small += (rl.count[kNumRL / 2 - 1 - q] + 31u) / 32u;
-        rl.item_base_mid[q] = items_mid;
-        items_mid += (rl.count[kNumRL - 1 - q] + 31u) / 32u;
-    }
-    rl.item_base_small[kNumRL / 2] = items_small;
-    rl.item_base_mid[kNumRL / 2] = items_mid;
-    uint32_t items = 0;
-    int q = 0;
-    for (int gi = kNumG - 1; gi >= 0; --gi) {
-        for (int wide = 1; wide >= 0; --wide) {
-            const int cl = gi + (wide ? kNumG : 0);
-            const uint32_t G = class_lanes(gi), rpb = 32u / G;
-            tab.lanes[cl] = G;
-            tab.rpb[cl] = rpb;
-            tab.inv[cl] = (65536u + G - 1u) / G;
-            tab.order[q] = (uint32_t)cl;
-            tab.item_base[q] = items;
-            items += (tab.count[cl] + rpb - 1u) / rpb;
-            ++q;
-        }
-    }
-    tab.item_base[kNumClasses] = items;
+    const Plan pl = make_plan(a, coverage, rl_max_slots());
+    const ClassTab &tab = pl.tab;
+    const RLTab &rl = pl.rl;
+    const uint32_t rl_max = pl.rl_max, items = pl.items, items_small = pl.items_small, items_mid = pl.items_mid;
 
-    scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, tab, rl, coverage, rl_max);
-    ++launches;
+    if (a.worklist_ready && rl_max == 0) {
+        // the lane-group worklist does not depend on the threshold: launch_worklist built it once for this CSR
+        if (cudaMemsetAsync(w.part_total, 0, sizeof(uint32_t) * w.n_parts, stream) != cudaSuccess) return -1;
+    } else {
+        scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, tab, rl, coverage, rl_max);
+        ++launches;
+    }
     if (a.rows.n_big) {
         // shared memory for the largest row (wide if any read is); rows beyond kCtaMaxSmemWords sort in a global slab
         uint64_t words = cta_words(a.max_k, a.rows.n_wide != 0);
@@ -1481,6 +1516,17 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     }
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
+}
+
+int launch_worklist(const DetectArgs &a, cudaStream_t stream) {
+    if (a.n_reads == 0) return 0;
+    size_t total = 0;
+    Work w = carve(a, a.rows.huge_keys, a.rows.n_big, a.rows.big_pairs, &total);
+    if (total > a.scratch_bytes) return -1;
+    if (cudaMemsetAsync(a.counters, 0, kNumCounters * sizeof(uint32_t), stream) != cudaSuccess) return -1;
+    const Plan pl = make_plan(a, 0u, 0u);
+    scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, pl.tab, pl.rl, 0u, 0u);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_classify(const uint32_t *len, const uint32_t *gap_ptr, const uint2 *gaps, uint32_t n_reads, double not_coverage,

@@ -110,6 +110,7 @@ struct yb_ctx {
     uint32_t flags = 0;
     uint32_t ingest_threads = 0;
     bool host_only = false;
+    bool worklist_ready = false;  // the lane-group worklist in d_scratch matches the uploaded CSR
     bool bulk_frozen = false;  // the CSR came straight from the parallel ingester: `pending` does not hold it
     std::string error;
 
@@ -698,6 +699,41 @@ int yb_overlap(yb_ctx *c, const char *id, size_t id_len, const uint32_t **iv_pai
     return YB_OK;
 }
 
+// The detect kernels' view of the uploaded CSR and of the result buffers.
+static int detect_args(yb_ctx *c, yb::DetectArgs *out) {
+    yb::DetectArgs a{};
+    a.iv = c->d_iv.p;
+    a.rowptr = c->d_rowptr.p;
+    a.len = c->d_len.p;
+    a.n_reads = c->n_reads;
+    a.n_iv = c->n_iv;
+    a.max_k = c->max_k;
+    a.worklist_ready = c->worklist_ready ? 1u : 0u;
+    a.rows = c->rows;
+    a.cls = c->d_cls.p;
+    a.gap_ptr = c->d_gap_ptr.p;
+    a.gaps = c->d_gaps.p;
+    a.bitmap = c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p;
+    a.counters = c->d_counters.p;
+    a.scratch = c->d_scratch.p;
+    a.scratch_bytes = c->d_scratch.cap;
+    if (c->ext_bitmap && c->ext_bitmap_bytes < c->bitmap_bytes())
+        return c->fail(YB_ERR_INVALID_ARGUMENT, "bound bitmap buffer too small (%zu < %zu bytes)", c->ext_bitmap_bytes, c->bitmap_bytes());
+    a.n_peers = c->n_peers;
+    if (c->n_peers) {
+        if (c->peer_slot_bytes < c->bitmap_bytes())
+            return c->fail(YB_ERR_INVALID_ARGUMENT, "peer slot too small (%zu < %zu bytes)", c->peer_slot_bytes, c->bitmap_bytes());
+        a.rank = c->peer_rank;
+        for (uint32_t p = 0; p < c->n_peers; ++p) {
+            a.peer_slot[p] = c->peer_gather[p] + (size_t)c->peer_rank * c->peer_slot_bytes;
+            a.peer_flag[p] = c->peer_flags[p];
+        }
+        a.bitmap = a.peer_slot[c->peer_rank];
+    }
+    *out = a;
+    return YB_OK;
+}
+
 // ---- staged device API -------------------------------------------------------------------------------
 int yb_upload(yb_ctx *c) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
@@ -749,6 +785,25 @@ int yb_upload(yb_ctx *c) {
     c->stats.kernel_launches += (uint64_t)vl;
     const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->rows);
     if (!c->d_scratch.reserve(sb)) return c->fail(YB_ERR_NOMEM, "device scratch allocation failed (%zu bytes)", sb);
+    {   // the size-class worklist of the lane-group tier depends on rowptr / len only: built once, here
+        c->worklist_ready = false;
+        if (!c->d_counters.reserve(yb::kNumCounters)) return c->fail(YB_ERR_NOMEM, "device allocation failed");
+        yb::DetectArgs a{};
+        a.iv = c->d_iv.p;
+        a.rowptr = c->d_rowptr.p;
+        a.len = c->d_len.p;
+        a.n_reads = c->n_reads;
+        a.n_iv = c->n_iv;
+        a.max_k = c->max_k;
+        a.rows = c->rows;
+        a.counters = c->d_counters.p;
+        a.scratch = c->d_scratch.p;
+        a.scratch_bytes = c->d_scratch.cap;
+        const int wl = yb::launch_worklist(a, c->stream);
+        if (wl < 0) return c->cuda_fail(cudaGetLastError(), "worklist kernel");
+        c->stats.kernel_launches += (uint64_t)wl;
+        c->worklist_ready = true;
+    }
     c->stats.h2d_bytes += sizeof(uint32_t) * (2 * n + 1) + sizeof(uint2) * m;
     c->stats.d2h_bytes += sizeof(yb::DevRowStats);
     c->uploaded = true;
@@ -769,34 +824,9 @@ int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *s
                                        c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p, c->d_counters.p, st);
     } else {
         if (!c->uploaded) return c->fail(YB_ERR_STATE, "yb_compute_device before yb_upload");
+        if (yb::rl_max_slots() != 0) c->worklist_ready = false;  // that step rewrites the worklist with its own classes
         yb::DetectArgs a{};
-        a.iv = c->d_iv.p;
-        a.rowptr = c->d_rowptr.p;
-        a.len = c->d_len.p;
-        a.n_reads = c->n_reads;
-        a.n_iv = c->n_iv;
-        a.max_k = c->max_k;
-        a.rows = c->rows;
-        a.cls = c->d_cls.p;
-        a.gap_ptr = c->d_gap_ptr.p;
-        a.gaps = c->d_gaps.p;
-        a.bitmap = c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p;
-        a.counters = c->d_counters.p;
-        a.scratch = c->d_scratch.p;
-        a.scratch_bytes = c->d_scratch.cap;
-        if (c->ext_bitmap && c->ext_bitmap_bytes < c->bitmap_bytes())
-            return c->fail(YB_ERR_INVALID_ARGUMENT, "bound bitmap buffer too small (%zu < %zu bytes)", c->ext_bitmap_bytes, c->bitmap_bytes());
-        a.n_peers = c->n_peers;
-        if (c->n_peers) {
-            if (c->peer_slot_bytes < c->bitmap_bytes())
-                return c->fail(YB_ERR_INVALID_ARGUMENT, "peer slot too small (%zu < %zu bytes)", c->peer_slot_bytes, c->bitmap_bytes());
-            a.rank = c->peer_rank;
-            for (uint32_t p = 0; p < c->n_peers; ++p) {
-                a.peer_slot[p] = c->peer_gather[p] + (size_t)c->peer_rank * c->peer_slot_bytes;
-                a.peer_flag[p] = c->peer_flags[p];
-            }
-            a.bitmap = a.peer_slot[c->peer_rank];
-        }
+        if (int rc = detect_args(c, &a)) return rc;
         launches = yb::launch_detect(a, coverage > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)coverage, not_coverage, st);
     }
     if (launches < 0) return c->cuda_fail(cudaGetLastError(), "kernel launch");

@@ -89,6 +89,7 @@ struct DetectArgs {
     uint32_t n_reads;
     uint32_t n_iv;
     uint32_t max_k;          // largest row (host knows it from the row pointers)
+    uint32_t worklist_ready; // launch_worklist has filled the lane-group worklist of this CSR (scratch is untouched since)
     RowStats rows;
     // outputs, resident in HBM
     uint8_t *cls;            // n_reads, yb_read_type
@@ -132,6 +133,15 @@ size_t detect_scratch_bytes(uint32_t n_reads, uint32_t n_iv, const RowStats &rs)
 // Per-row contributions to RowStats (the engine sums them over the rows at freeze time).
 uint64_t huge_keys_for_row(uint64_t k);
 uint64_t big_pairs_for_row(uint64_t k);
+
+// Builds, once per uploaded CSR, the size-class worklist of the lane-group tier (16 bytes per read: row, first interval,
+// k, class, length) in the scratch buffer. It depends on rowptr / len only, not on the threshold, so like the interval
+// validation it belongs to the upload (the reference builds its read index, a hash map, while it ingests). With
+// DetectArgs::worklist_ready set, launch_detect skips its scatter kernel. Returns launches or -1.
+int launch_worklist(const DetectArgs &a, cudaStream_t stream);
+// Where the opt-in row-per-lane tier ends (YB_RL_MAX_SLOTS, read at every call; 0 = off). A step that runs with the tier
+// on rewrites the worklist with its own classes, so the caller must drop worklist_ready until the next upload.
+uint32_t rl_max_slots();
 
 // Enqueues one whole detect step on `stream`. Returns the number of kernel launches enqueued, or -1
 // on a launch error.
