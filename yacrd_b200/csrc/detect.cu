@@ -1096,7 +1096,10 @@ __global__ void __launch_bounds__(1024) scan_parts_kernel(DetectArgs a, Work w) 
     }
 }
 
-__global__ void __launch_bounds__(kPartRows) order_kernel(DetectArgs a, Work w, double not_cov) {
+#ifndef YB_ORDER_MIN_CTAS
+#define YB_ORDER_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(kPartRows, YB_ORDER_MIN_CTAS) order_kernel(DetectArgs a, Work w, double not_cov) {
     __shared__ uint32_t s_warp[kPartRows / 32], s_hist[kPartRows / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t part = blockIdx.x, r = part * kPartRows + tid;
