@@ -844,53 +844,81 @@ constexpr size_t kSortSmemBytes = kWarpSmemBytes * kSortWarps;
 #endif
 constexpr uint32_t kTpPitch = 33;  // words between consecutive slots of Tp
 // per warp: Tp (nmax slots + the +inf key behind the last one) and the 32 copy descriptors
-__host__ __device__ constexpr size_t rl_tp_bytes(uint32_t nmax) { return ((nmax + 1u) * kTpPitch * sizeof(uint32_t) + 15u) & ~(size_t)15; }
-__host__ __device__ constexpr size_t rl_warp_smem(uint32_t nmax) { return rl_tp_bytes(nmax) + 32u * sizeof(uint2); }
+// Tp: one leading dump slot (local slot -1 of a row that starts at an odd interval lands there), nmax slots, the +inf key
+__host__ __device__ constexpr size_t rl_tp_bytes(uint32_t nmax) { return ((nmax + 2u) * kTpPitch * sizeof(uint32_t) + 15u) & ~(size_t)15; }
+__host__ __device__ constexpr size_t rl_warp_smem(uint32_t nmax) { return rl_tp_bytes(nmax) + 32u * sizeof(uint4); }
 
-// Transposing copy of the batch's rows into Tp: row j's interval t -> Tp[t][j] as begin | end << 16.
-// desc[j] = {first interval, k} of row j, read back as broadcasts. CH = 32-interval chunks a row of the class can have.
-template <int CH>
-__device__ __forceinline__ void rl_stage(const DetectArgs &a, uint32_t *Tp, const uint2 *desc) {
-    constexpr int RB = CH <= 2 ? 8 : 4;  // rows whose loads are in flight together (the loads of a group are issued
-                                         // before any of its stores: shared-memory stores would otherwise fence the
-                                         // next descriptor read and serialise the rows on the load latency)
+// Transposing copy of the batch's rows into Tp: row j's interval t -> Tp[1 + t][j] as begin | end << 16.
+// desc[j] = {aligned first interval / 2, k + o, 132 o, first interval} of row j (o = first interval & 1), read back as
+// broadcasts. Rows of at most 64 slots: ONE aligned 16-byte load per lane and row (two intervals), two stores; lanes
+// beyond the row's end store stale registers (no second predicate) that the sentinel loop overwrites.
+__device__ __forceinline__ void rl_stage16(const DetectArgs &a, uint32_t *Tp, const uint4 *desc) {
+    constexpr int RB = 8;  // rows whose loads are in flight together (all loads of a group are issued before its stores:
+                           // a shared-memory store would otherwise fence the next descriptor read)
     const uint32_t lane = lane_id();
-    const uint2 *src_lane = a.iv + lane;
-    uint32_t *dst_lane = Tp + lane * kTpPitch;
+    const uint4 *src_lane = reinterpret_cast<const uint4 *>(a.iv) + lane;
+    char *dst_lane = reinterpret_cast<char *>(Tp + (2u * lane + 1u) * kTpPitch);
+    uint4 v[RB] = {};  // zeroed once per batch: a lane beyond a row's end stores whatever an earlier row left there
 #pragma unroll 1
     for (int j0 = 0; j0 < 32; j0 += RB) {
-        uint2 d[RB], v[RB][CH];
-#pragma unroll
-        for (int r = 0; r < RB; ++r) d[r] = desc[j0 + r];
+        uint32_t off[RB];
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
+            const uint4 d = desc[j0 + r];
+            off[r] = d.z;
+            if (2u * lane < d.y) v[r] = __ldg(src_lane + d.x);
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(dst_lane - off[r]) + j0 + r;
+            dst[0] = __byte_perm(v[r].x, v[r].y, 0x5410);
+            dst[kTpPitch] = __byte_perm(v[r].z, v[r].w, 0x5410);
+        }
+    }
+}
+
+// The same for rows of up to 128 slots: CH chunks of 32 intervals, one 8-byte load per lane, row and chunk.
+template <int CH>
+__device__ __forceinline__ void rl_stage(const DetectArgs &a, uint32_t *Tp, const uint4 *desc) {
+    constexpr int RB = 4;
+    const uint32_t lane = lane_id();
+    const uint2 *src_lane = a.iv + lane;
+    uint32_t *dst_lane = Tp + (lane + 1u) * kTpPitch;
+#pragma unroll 1
+    for (int j0 = 0; j0 < 32; j0 += RB) {
+        uint2 v[RB][CH];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const uint4 d = desc[j0 + r];
+            const uint32_t k = d.y - (d.w & 1u);
 #pragma unroll
             for (int ch = 0; ch < CH; ++ch) {
                 v[r][ch] = make_uint2(0u, 0u);
-                if (lane + 32u * ch < d[r].y) v[r][ch] = __ldg(src_lane + d[r].x + 32 * ch);
+                if (lane + 32u * ch < k) v[r][ch] = __ldg(src_lane + d.w + 32 * ch);
             }
         }
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
 #pragma unroll
-            for (int ch = 0; ch < CH; ++ch)
-                if (lane + 32u * ch < d[r].y) dst_lane[32 * ch * kTpPitch + j0 + r] = __byte_perm(v[r][ch].x, v[r][ch].y, 0x5410);
+            for (int ch = 0; ch < CH; ++ch) dst_lane[32 * ch * kTpPitch + j0 + r] = __byte_perm(v[r][ch].x, v[r][ch].y, 0x5410);
         }
     }
 }
 
 template <int N>
-__device__ __forceinline__ void rl_batch(const DetectArgs &a, const Work &w, uint32_t *Tp, uint2 *desc, const uint4 rec, uint32_t c,
+__device__ __forceinline__ void rl_batch(const DetectArgs &a, const Work &w, uint32_t *Tp, uint4 *desc, const uint4 rec, uint32_t c,
                                          uint2 &chunk) {
     constexpr int W = N / 16 + ((N % 16) ? 1 : 0);  // 32-bit words of Z: 16 slots each
     const uint32_t lane = lane_id();
     const bool valid = (rec.z & kRecValid) != 0u;
     const uint32_t k = valid ? (rec.z & 0xFFFFu) : 0u, len = rec.w;
     const uint32_t cp = min(c, k);
-    desc[lane] = make_uint2(rec.y, k);
+    desc[lane] = make_uint4(rec.y >> 1, k + (rec.y & 1u), (rec.y & 1u) * kTpPitch * 4u, rec.y);
     __syncwarp();
-    rl_stage<(N + 31) / 32>(a, Tp, desc);
-    uint32_t *col = Tp + lane;  // the lane's row: slot t at col[t * kTpPitch]
+    if (N <= 64) rl_stage16(a, Tp, desc);
+    else rl_stage<(N + 31) / 32>(a, Tp, desc);
+    __syncwarp();
+    uint32_t *col = Tp + kTpPitch + lane;  // the lane's row: slot t at col[t * kTpPitch]
     // sentinels behind the row's intervals: c' + 1 keys (+inf, 0), then (+inf, +inf)
     for (uint32_t t = k; t < (uint32_t)N; ++t) col[t * kTpPitch] = t <= k + cp ? 0x0000FFFFu : FULL;
     __syncwarp();
@@ -1005,7 +1033,7 @@ __global__ void __launch_bounds__(32 * (MID ? YB_RL_WARPS_MID : YB_RL_WARPS_SMAL
     constexpr int NQ = kNumRL / 2;
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     uint32_t *Tp = reinterpret_cast<uint32_t *>(smem_raw + wid * rl_warp_smem(NMAX));
-    uint2 *desc = reinterpret_cast<uint2 *>(smem_raw + wid * rl_warp_smem(NMAX) + rl_tp_bytes(NMAX));
+    uint4 *desc = reinterpret_cast<uint4 *>(smem_raw + wid * rl_warp_smem(NMAX) + rl_tp_bytes(NMAX));
     const uint32_t *item_base = MID ? tab.item_base_mid : tab.item_base_small;
     const uint32_t n_items = item_base[NQ];
     // Static schedule: warp g of the grid takes batches g, g + G, g + 2 G, ... Batches of one class cost the same and the
