@@ -163,8 +163,10 @@ int yb_init_report(yb_ctx *ctx, const char *path);
 int yb_init_report_buffer(yb_ctx *ctx, const char *text, size_t n_bytes);
 
 /* ---- staged device API (what yb_compute_all_bad_part is made of) ---------------------------- */
-/* Freeze the host store into a CSR (flat (begin,end) buffer + row pointers + lengths), validate
- * 0 <= begin < end <= length, and copy it to HBM. This is the get_overlaps boundary (stack.rs:149). */
+/* Freeze the host store into a CSR (flat (begin,end) buffer + row pointers + lengths) and copy it to HBM;
+ * then, once per uploaded CSR and on the device: row statistics, the test 0 <= begin < end <= length of
+ * every interval (its count is reported by yb_download as YB_ERR_MALFORMED_INTERVAL) and the size-class
+ * worklist of the rows (16 bytes per read). This is the get_overlaps boundary (stack.rs:149). */
 int yb_upload(yb_ctx *ctx);
 /* Kernels only; inputs and outputs stay resident in HBM. `stream` is a cudaStream_t (NULL = the
  * context's own stream); the call is asynchronous with respect to the host. */
