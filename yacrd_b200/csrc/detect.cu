@@ -1504,6 +1504,7 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, tab, rl, coverage, rl_max);
         ++launches;
     }
+    bool forked = false;
     if (a.rows.n_big) {
         // shared memory for the largest row (wide if any read is); rows beyond kCtaMaxSmemWords sort in a global slab
         uint64_t words = cta_words(a.max_k, a.rows.n_wide != 0);
@@ -1513,8 +1514,12 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         if (per_sm > 8u) per_sm = 8u;
         uint32_t grid = (uint32_t)n_sm * per_sm;
         if (grid > a.rows.n_big) grid = (uint32_t)a.rows.n_big;
-        big_kernel<<<grid, kCtaThreads, words * sizeof(uint32_t), stream>>>(a, w, coverage, (uint32_t)words);
+        // the few long rows run on a side stream, beside the register tier (both only append to the staging buffer)
+        forked = a.side_stream && a.ev_fork && a.ev_join && cudaEventRecord(a.ev_fork, stream) == cudaSuccess &&
+                 cudaStreamWaitEvent(a.side_stream, a.ev_fork, 0) == cudaSuccess;
+        big_kernel<<<grid, kCtaThreads, words * sizeof(uint32_t), forked ? a.side_stream : stream>>>(a, w, coverage, (uint32_t)words);
         ++launches;
+        if (forked && cudaEventRecord(a.ev_join, a.side_stream) != cudaSuccess) return -1;
     }
     if (items) {
         uint32_t grid = (uint32_t)(n_sm * occ_sort);
@@ -1537,6 +1542,7 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         rl_kernel<false><<<grid, kSmallThreads, kSmallSmem, stream>>>(a, w, rl, coverage);
         ++launches;
     }
+    if (forked && cudaStreamWaitEvent(stream, a.ev_join, 0) != cudaSuccess) return -1;
     scan_parts_kernel<<<1, 1024, 0, stream>>>(a, w);
     ++launches;
     order_kernel<<<w.n_parts, kPartRows, 0, stream>>>(a, w, not_coverage);

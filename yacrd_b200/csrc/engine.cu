@@ -106,6 +106,8 @@ inline char *put_u64(char *p, uint64_t v) {
 struct yb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;          // the CTA tier (rows with k > 512) runs here, beside the register tier
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t read_buffer_size = 8192;
     uint32_t flags = 0;
     uint32_t ingest_threads = 0;
@@ -332,6 +334,14 @@ yb_ctx *yb_create(const yb_opts *opts) {
         delete c;
         return nullptr;
     }
+    // optional: without them the tiers simply run one after the other
+    if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (c->side_stream) cudaStreamDestroy(c->side_stream);
+        c->side_stream = nullptr;
+    }
     return c;
 }
 
@@ -349,6 +359,12 @@ void yb_destroy(yb_ctx *c) {
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
+    if (c->side_stream) {
+        cudaStreamSynchronize(c->side_stream);
+        cudaStreamDestroy(c->side_stream);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     c->h_rowptr.release();
     c->h_len.release();
     c->h_iv.release();
@@ -715,6 +731,9 @@ static int detect_args(yb_ctx *c, yb::DetectArgs *out) {
     a.gaps = c->d_gaps.p;
     a.bitmap = c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p;
     a.counters = c->d_counters.p;
+    a.side_stream = c->side_stream;
+    a.ev_fork = c->ev_fork;
+    a.ev_join = c->ev_join;
     a.scratch = c->d_scratch.p;
     a.scratch_bytes = c->d_scratch.cap;
     if (c->ext_bitmap && c->ext_bitmap_bytes < c->bitmap_bytes())

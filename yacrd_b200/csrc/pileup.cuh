@@ -101,6 +101,10 @@ struct DetectArgs {
     uint8_t *peer_slot[16];  // peer p's gather buffer + rank * slot_bytes
     uint32_t *peer_flag[16]; // peer p's flag array (word q: last step rank q finished; word 31: own step counter)
     uint32_t *counters;      // kNumCounters
+    // host side only: a second stream and two events so that the CTA tier (rows with k > 512) runs beside the register
+    // tier instead of in front of it (null: same stream, one after the other)
+    cudaStream_t side_stream;
+    cudaEvent_t ev_fork, ev_join;
     // scratch
     void *scratch;
     size_t scratch_bytes;
