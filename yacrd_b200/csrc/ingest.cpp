@@ -351,42 +351,75 @@ bool ingest_buffer_parallel(const char *text, size_t n, int format, int threads,
             for (int ct = 0; ct < T; ++ct) {
                 Chunk &c = chunks[ct];
                 const char *base = cut[ct];
-                for (const uint32_t code : c.by_part[pi]) {
-                    Rec &r = c.recs[code >> 1];
-                    const bool side = code & 1u;
-                    const char *s = base + (side ? r.offb : r.offa);
-                    const uint32_t sn = side ? r.nb : r.na;
-                    const uint64_t h = hash_id(s, sn);
-                    size_t mask = pt.slots.size() - 1, pos = (size_t)h & mask;
-                    uint32_t found = 0xFFFFFFFFu;
-                    for (;; pos = (pos + 1) & mask) {
-                        const uint32_t e = pt.slots[pos];
-                        if (e == 0xFFFFFFFFu) break;
-                        if (pt.ent[e].n == sn && memcmp(pt.ent[e].id, s, sn) == 0) {
-                            found = e;
-                            break;
+                // A lookup is three dependent cache misses (slot -> entry -> the entry's id bytes in the text). They are
+                // taken out of the critical path by walking the list in blocks: hashes and slot prefetches for the
+                // whole block, then entry prefetches, then id prefetches, then the real (sequential, order-preserving)
+                // probes, which now hit the cache. Prefetches are hints only: entries inserted by the block itself are
+                // still found by the probes.
+                const std::vector<uint32_t> &list = c.by_part[pi];
+                constexpr size_t kBlock = 16;
+                for (size_t b0 = 0; b0 < list.size() && !pt.overflow; b0 += kBlock) {
+                    const size_t bn = std::min(kBlock, list.size() - b0);
+                    const char *bs[kBlock];
+                    uint32_t bl[kBlock];
+                    uint64_t bh[kBlock];
+                    {
+                        const size_t mask = pt.slots.size() - 1;
+                        for (size_t i = 0; i < bn; ++i) {
+                            const uint32_t code = list[b0 + i];
+                            const Rec &r = c.recs[code >> 1];
+                            bs[i] = base + ((code & 1u) ? r.offb : r.offa);
+                            bl[i] = (code & 1u) ? r.nb : r.na;
+                            bh[i] = hash_id(bs[i], bl[i]);
+                            __builtin_prefetch(&pt.slots[(size_t)bh[i] & mask]);
+                        }
+                        for (size_t i = 0; i < bn; ++i) {
+                            const uint32_t e = pt.slots[(size_t)bh[i] & mask];
+                            if (e != 0xFFFFFFFFu) __builtin_prefetch(&pt.ent[e]);
+                        }
+                        for (size_t i = 0; i < bn; ++i) {
+                            const uint32_t e = pt.slots[(size_t)bh[i] & mask];
+                            if (e != 0xFFFFFFFFu) __builtin_prefetch(pt.ent[e].id);
                         }
                     }
-                    if (found == 0xFFFFFFFFu) {
-                        found = (uint32_t)pt.ent.size();
-                        if (found >= (1u << 26)) {
-                            pt.overflow = true;
-                            break;
-                        }
-                        pt.ent.push_back(Entry{(rec_base[ct] + (code >> 1)) * 2 + (side ? 1u : 0u), s, sn, side ? r.lb : r.la});
-                        pt.slots[pos] = found;
-                        if ((pt.ent.size() + 1) * 10 > pt.slots.size() * 6) {  // grow
-                            std::vector<uint32_t> ns(pt.slots.size() * 2, 0xFFFFFFFFu);
-                            const size_t m2 = ns.size() - 1;
-                            for (uint32_t i = 0; i < pt.ent.size(); ++i) {
-                                size_t q = (size_t)hash_id(pt.ent[i].id, pt.ent[i].n) & m2;
-                                while (ns[q] != 0xFFFFFFFFu) q = (q + 1) & m2;
-                                ns[q] = i;
+                    for (size_t i = 0; i < bn; ++i) {
+                        const uint32_t code = list[b0 + i];
+                        Rec &r = c.recs[code >> 1];
+                        const bool side = code & 1u;
+                        const char *s = bs[i];
+                        const uint32_t sn = bl[i];
+                        const uint64_t h = bh[i];
+                        size_t mask = pt.slots.size() - 1, pos = (size_t)h & mask;
+                        uint32_t found = 0xFFFFFFFFu;
+                        for (;; pos = (pos + 1) & mask) {
+                            const uint32_t e = pt.slots[pos];
+                            if (e == 0xFFFFFFFFu) break;
+                            if (pt.ent[e].n == sn && memcmp(pt.ent[e].id, s, sn) == 0) {
+                                found = e;
+                                break;
                             }
-                            pt.slots.swap(ns);
                         }
+                        if (found == 0xFFFFFFFFu) {
+                            found = (uint32_t)pt.ent.size();
+                            if (found >= (1u << 26)) {
+                                pt.overflow = true;
+                                break;
+                            }
+                            pt.ent.push_back(Entry{(rec_base[ct] + (code >> 1)) * 2 + (side ? 1u : 0u), s, sn, side ? r.lb : r.la});
+                            pt.slots[pos] = found;
+                            if ((pt.ent.size() + 1) * 10 > pt.slots.size() * 6) {  // grow
+                                std::vector<uint32_t> ns(pt.slots.size() * 2, 0xFFFFFFFFu);
+                                const size_t m2 = ns.size() - 1;
+                                for (uint32_t q2 = 0; q2 < pt.ent.size(); ++q2) {
+                                    size_t q = (size_t)hash_id(pt.ent[q2].id, pt.ent[q2].n) & m2;
+                                    while (ns[q] != 0xFFFFFFFFu) q = (q + 1) & m2;
+                                    ns[q] = q2;
+                                }
+                                pt.slots.swap(ns);
+                            }
+                        }
+                        (side ? r.rb : r.ra) = found | ((uint32_t)pi << 26);  // partition in the top 6 bits
                     }
-                    (side ? r.rb : r.ra) = found | ((uint32_t)pi << 26);  // partition in the top 6 bits
                 }
             }
         }
