@@ -571,7 +571,7 @@ int yb_init_buffer(yb_ctx *c, const char *text, size_t n_bytes, int format) {
         if (threads > 32) threads = 32;
         if (n_bytes < (1u << 20)) threads = 1;
     }
-    if (threads > 1 && c->total_reads() == 0 && !c->indexed && !c->from_report && c->pending.empty()) {
+    if (threads >= 1 && n_bytes >= (1u << 16) && c->total_reads() == 0 && !c->indexed && !c->from_report && c->pending.empty()) {
         yb::BulkIds ids;
         if (!yb::ingest_buffer_parallel(text, n_bytes, format, threads, alloc_csr_sink, c, &ids, &err))
             return c->fail(err.code, "%s", err.message.c_str());
