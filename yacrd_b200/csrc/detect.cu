@@ -38,6 +38,7 @@
 //                    uniform parts), staging -> ordered bad-region CSR, classification, 2-bit bitmap, histogram.
 #include "pileup.cuh"
 #include "sortnets.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace yb {
@@ -86,7 +87,12 @@ constexpr uint32_t kSortThreads = kSortWarps * 32;
 #ifndef YB_SORT_MIN_CTAS
 #define YB_SORT_MIN_CTAS (20 / YB_SORT_WARPS)
 #endif
-constexpr uint32_t kBufIntervals = 576;        // max over classes of floor(32/G) * (16 G + 2) row slots
+#ifndef YB_BUF_INTERVALS
+#define YB_BUF_INTERVALS 528
+#endif
+constexpr uint32_t kBufIntervals = YB_BUF_INTERVALS;  // row slots of a slab buffer. A batch holds min(floor(32 / G), floor(kBufIntervals /
+                                                      // (16 G + 2))) rows: 528 fits every class but G = 1 (29 rows instead of 32) and
+                                                      // G = 2 (15 instead of 16), and lets 20 instead of 18 warps share an SM
 constexpr uint32_t kScatterRows = 1024;        // rows per CTA of scatter_kernel
 constexpr uint32_t kPartShift = 8, kPartRows = 1u << kPartShift;  // rows per CTA of order_kernel
 constexpr uint32_t kStageChunk = 1024;       // pairs a warp reserves in the staging buffer per atomic
@@ -1399,7 +1405,7 @@ Plan make_plan(const DetectArgs &a, uint32_t coverage, uint32_t rl_max) {
     for (int gi = kNumG - 1; gi >= 0; --gi) {
         for (int wide = 1; wide >= 0; --wide) {
             const int cl = gi + (wide ? kNumG : 0);
-            const uint32_t G = class_lanes(gi), rpb = 32u / G;
+            const uint32_t G = class_lanes(gi), rpb = std::min(32u / G, kBufIntervals / (16u * G + 2u));
             tab.lanes[cl] = G;
             tab.rpb[cl] = rpb;
             tab.inv[cl] = (65536u + G - 1u) / G;
