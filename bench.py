@@ -362,7 +362,10 @@ def main():
                        else "L2 flushed (256 MB memset) before every timed step; steps timed individually",
                        "classes_rank0": dict(zip(["NotBad", "Chimeric", "NotCovered"], class_counts)),
                        "gaps_rank0": n_gaps_local, "gen_seconds": round(t_gen, 2),
-                       "launch": ("one CUDA graph per step" + (" (kernels) + eager NCCL all-gather" if use_dist and pg is None else "")) if graph is not None else "eager launches"},
+                       "launch": ("one CUDA graph per step" + (" (kernels) + eager NCCL all-gather" if use_dist and pg is None else "")) if graph is not None else "eager launches",
+                       "per_upload": "once per uploaded CSR, outside the device-resident step and inside e2e: row statistics, "
+                                     "interval validation (0 <= b < e <= len) and the size-class worklist (16 B per read), "
+                                     "0.27 ms of kernels at 2 M reads (profiles/r1_v8_launches.csv)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "rank 0's shard; duration = whole step (CUDA events on the launching stream)"},
