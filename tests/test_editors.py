@@ -188,33 +188,35 @@ def test_editor_errors(tmp_path):
     assert e.value.kind == "ReadingError"
     with pytest.raises(ValueError):
         yb.filter(bad, out, bp, 0.4)  # not the not_coverage the classes were computed with
-    bz = str(tmp_path / "reads.fastq.bz2")
-    open(bz, "wb").write(b"BZh91AY&SY" + b"\0" * 32)
-    with pytest.raises(yb.YacrdError) as e:
-        yb.filter(bz, out, bp, 0.8)  # util.rs:57-87 reads bzip2 / xz too; this build only gzip
-    assert e.value.kind == "CantReadFile"
     fm.close()
 
 
 @pytest.mark.gpu
-def test_gzip_input_keeps_its_compression(tmp_path):
-    """util.rs:57-87: compression is sniffed from the magic number and the output keeps the input's; here gzip only."""
+@pytest.mark.parametrize("codec", ["gz", "bz2", "xz"])
+def test_compressed_input_keeps_its_compression(tmp_path, codec):
+    """util.rs:57-87: compression is sniffed from the magic number and the output keeps the input's codec (level 1)."""
+    import bz2
+    import lzma
     import yacrd_b200 as yb
-    paf_gz = str(tmp_path / "overlaps.paf.gz")
-    with gzip.open(paf_gz, "wb") as fh:
-        fh.write(open(os.path.join(GOLDEN, "c1_overlaps.paf"), "rb").read())
+    pack = {"gz": gzip.compress, "bz2": bz2.compress, "xz": lzma.compress}[codec]
+    unpack = {"gz": gzip.decompress, "bz2": bz2.decompress, "xz": lzma.decompress}[codec]
+    magic = {"gz": b"\x1f\x8b", "bz2": b"BZh", "xz": b"\xfd7zXZ\x00"}[codec]
+    paf = str(tmp_path / ("overlaps.paf." + codec))
+    open(paf, "wb").write(pack(open(os.path.join(GOLDEN, "c1_overlaps.paf"), "rb").read()))
+    reads = str(tmp_path / ("reads.fastq." + codec))
+    open(reads, "wb").write(pack(reads_fastq()))
     fm = yb.FullMemory()
-    fm.init(paf_gz)
+    fm.init(paf)
     bp = yb.FromOverlap(fm, 0, 0.8)
     bp.compute_all_bad_part()
     want = sorted(l for l in open(os.path.join(GOLDEN, "c1_truth.sorted.yacrd")).read().split("\n") if l)
     assert sorted(bp.report_lines()) == want
     for op, fn in (("scrubb", yb.scrubbing), ("filter", yb.filter), ("extract", yb.extract), ("split", yb.split)):
-        out = str(tmp_path / ("reads.%s.fastq.gz" % op))
-        fn(os.path.join(GOLDEN, "c1_reads.fastq.gz"), out, bp, 0.8)
+        out = str(tmp_path / ("reads.%s.fastq.%s" % (op, codec)))
+        fn(reads, out, bp, 0.8)
         raw = open(out, "rb").read()
-        assert raw[:2] == b"\x1f\x8b"
-        assert hashlib.sha256(gzip.decompress(raw)).hexdigest() == DIGESTS[op]["sha256"]
+        assert raw.startswith(magic)
+        assert hashlib.sha256(unpack(raw)).hexdigest() == DIGESTS[op]["sha256"]
     fm.close()
 
 

@@ -9,6 +9,7 @@ import pytest
 
 import yacrd_b200 as yb
 from oracle import yacrd_oracle as o
+from tests.conftest import GOLDEN
 
 
 def _random_paf(rng, n_records, n_ids, m4=False, crlf=False, blank_every=0):
@@ -114,3 +115,29 @@ def test_host_only_context_cannot_compute():
         yb.FromOverlap(fm, 0, 0.8).compute_all_bad_part()
     assert e.value.kind == "Cuda"
     fm.close()
+
+
+@pytest.mark.parametrize("codec", ["gz", "bz2", "xz"])
+def test_compressed_overlap_files_are_sniffed_by_magic_number(tmp_path, codec):
+    """util.rs:57-87 (niffler): the compression of the input is detected from its first bytes, not from its name."""
+    import bz2
+    import gzip
+    import lzma
+    raw = open(os.path.join(GOLDEN, "c1_overlaps.paf"), "rb").read()
+    packed = {"gz": gzip.compress, "bz2": bz2.compress, "xz": lzma.compress}[codec](raw)
+    path = str(tmp_path / "overlaps.paf")  # no suffix that tells
+    open(path, "wb").write(packed)
+    a = yb.FullMemory(host_only=True)
+    a.init(path)
+    b = yb.FullMemory(host_only=True)
+    b.init(os.path.join(GOLDEN, "c1_overlaps.paf"))
+    assert a.read_ids() == b.read_ids()
+    for rid in b.read_ids()[:40]:
+        assert a.overlap(rid) == b.overlap(rid) and a.length(rid) == b.length(rid)
+    a.close()
+    b.close()
+    open(path, "wb").write(packed[: len(packed) // 2])  # a truncated stream is an error, not a short file
+    c = yb.FullMemory(host_only=True)
+    with pytest.raises(yb.YacrdError):
+        c.init(path)
+    c.close()

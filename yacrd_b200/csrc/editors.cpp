@@ -10,13 +10,12 @@
 // first space and written back with one space; fasta sequences are re-wrapped at 80 columns; fasta records cut by
 // scrubb / split lose their description, fastq records keep it (scrubbing.rs:139-153 vs 211-224).
 // Overlap files (filter / extract only) pass through line by line; csv quoting is not interpreted.
-// Compression (util.rs:57-87, niffler): gzip input is read through zlib and the output is gzip again (level 1, as
-// util.rs:84 asks); bzip2 / xz are refused (no development headers in this image).
+// Compression (util.rs:57-87, niffler): the input's codec is sniffed from its magic number (gzip, bzip2, xz) and the
+// output is written with the same codec at level 1, as util.rs:84 asks (codec.cpp).
 #include <errno.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
-#include <zlib.h>
 
 #include <string>
 #include <vector>
@@ -45,7 +44,7 @@ struct Err {
 // Buffered line reader: lines end with '\n' (a preceding '\r' is dropped); the last line may lack the terminator.
 class LineReader {
   public:
-    LineReader(gzFile f, size_t cap) : f_(f), buf_(cap < (1u << 16) ? (1u << 16) : cap) {}
+    LineReader(ByteSource *f, size_t cap) : f_(f), buf_(cap < (1u << 16) ? (1u << 16) : cap) {}
     // false at end of input. *line stays valid until the next call.
     bool next(std::string *line) {
         line->clear();
@@ -72,24 +71,13 @@ class LineReader {
         return any;
     }
     bool io_error() const { return bad_; }
-    // first bytes of the stream without consuming them (compression sniffing); call before next()
-    size_t peek(unsigned char *out, size_t n) {
-        if (pos_ == end_) {
-            end_ = fill();
-            pos_ = 0;
-        }
-        const size_t m = end_ - pos_ < n ? end_ - pos_ : n;
-        memcpy(out, buf_.data() + pos_, m);
-        return m;
-    }
-
   private:
-    size_t fill() {  // zlib reads plain files as they are and inflates gzip ones
-        const int got = gzread(f_, buf_.data(), (unsigned)buf_.size());
+    size_t fill() {
+        const long got = f_->read(buf_.data(), buf_.size());
         if (got < 0) bad_ = true;
         return got > 0 ? (size_t)got : 0;
     }
-    gzFile f_;
+    ByteSource *f_;
     std::vector<char> buf_;
     size_t pos_ = 0, end_ = 0;
     bool bad_ = false;
@@ -97,11 +85,11 @@ class LineReader {
 
 class Out {
   public:
-    Out(FILE *f, gzFile g, size_t cap) : f_(f), g_(g), buf_(cap < (1u << 16) ? (1u << 16) : cap) {}
+    Out(ByteSink *f, size_t cap) : f_(f), buf_(cap < (1u << 16) ? (1u << 16) : cap) {}
     void put(const char *p, size_t n) {
         if (n > buf_.size() - len_) flush();
         if (n > buf_.size()) {
-            ok_ = ok_ && write(p, n);
+            ok_ = ok_ && f_->write(p, n);
             return;
         }
         memcpy(buf_.data() + len_, p, n);
@@ -110,25 +98,13 @@ class Out {
     void put(const std::string &s) { put(s.data(), s.size()); }
     void put(char ch) { put(&ch, 1); }
     void flush() {
-        if (len_) ok_ = ok_ && write(buf_.data(), len_);
+        if (len_) ok_ = ok_ && f_->write(buf_.data(), len_);
         len_ = 0;
     }
     bool ok() const { return ok_; }
 
   private:
-    bool write(const char *p, size_t n) {
-        if (g_) {
-            for (size_t at = 0; at < n;) {
-                const unsigned part = n - at > (1u << 30) ? (1u << 30) : (unsigned)(n - at);
-                if (gzwrite(g_, p + at, part) != (int)part) return false;
-                at += part;
-            }
-            return true;
-        }
-        return fwrite(p, 1, n, f_) == n;
-    }
-    FILE *f_;
-    gzFile g_;
+    ByteSink *f_;
     std::vector<char> buf_;
     size_t len_ = 0;
     bool ok_ = true;
@@ -368,34 +344,26 @@ int run_editor(yb_ctx *ctx, int op, const char *input_path, const char *output_p
     if (t == 'y' || ((t == 'p' || t == 'm') && (op == YB_EDIT_SCRUBB || op == YB_EDIT_SPLIT)))
         return done(err.set(YB_ERR_WRONG_FORMAT, "Can't run %s on %s file %s", kOpName[op], t == 'y' ? "yacrd" : (t == 'p' ? "paf" : "m4"),
                             input_path));
-    gzFile fi = gzopen(input_path, "rb");
-    if (!fi) return done(err.set(YB_ERR_CANT_READ_FILE, "Can't open file %s: %s", input_path, strerror(errno)));
-    gzbuffer(fi, 1u << 18);
+    Codec codec = kPlain;
+    std::string why;
+    ByteSource *fi = open_source(input_path, &codec, &why);
+    if (!fi) return done(err.set(YB_ERR_CANT_READ_FILE, "%s", why.c_str()));
+    ByteSink *fo = open_sink(output_path, codec, &why);  // the output keeps the input's compression (util.rs:84)
+    if (!fo) {
+        delete fi;
+        return done(err.set(YB_ERR_CANT_WRITE_FILE, "%s", why.c_str()));
+    }
     LineReader in(fi, buffer_size);
-    unsigned char magic[6] = {0};
-    const size_t got = in.peek(magic, sizeof magic);
-    const bool gz = gzdirect(fi) == 0;  // niffler sniffs the magic number; the output keeps the input's compression
-    if (!gz && ((got >= 3 && !memcmp(magic, "BZh", 3)) || (got >= 6 && !memcmp(magic, "\xfd" "7zXZ\0", 6)))) {
-        gzclose(fi);
-        return done(err.set(YB_ERR_CANT_READ_FILE, "%s is bzip2- or xz-compressed; only gzip is read by this build", input_path));
-    }
-    FILE *fo = nullptr;
-    gzFile go = nullptr;
-    if (gz) go = gzopen(output_path, "wb1");  // util.rs:84: niffler::compression::Level::One
-    else fo = fopen(output_path, "wb");
-    if (!fo && !go) {
-        gzclose(fi);
-        return done(err.set(YB_ERR_CANT_WRITE_FILE, "Can't create file %s: %s", output_path, strerror(errno)));
-    }
-    Out out(fo, go, buffer_size);
+    Out out(fo, buffer_size);
     Lookup look{ctx};
     int rc;
     if (t == 'a') rc = edit_fasta(op, in, out, look, &err);
     else if (t == 'q') rc = edit_fastq(op, in, out, look, &err);
     else rc = edit_overlaps(op, t == 'p' ? '\t' : ' ', t == 'p' ? 5 : 1, in, out, look, &err);
     out.flush();
-    gzclose(fi);
-    const bool wrote = (go ? gzclose(go) == Z_OK : fclose(fo) == 0) && out.ok();
+    delete fi;
+    const bool wrote = fo->close() && out.ok();
+    delete fo;
     if (rc == YB_OK && !wrote) rc = err.set(YB_ERR_WRITING, "Writing of the file %s failed", output_path);
     if (rc != YB_OK && err.msg.empty()) return rc;  // the context already holds the message (yb_get_bad_part)
     return done(rc);

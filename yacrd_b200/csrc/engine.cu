@@ -8,7 +8,6 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <sys/mman.h>
-#include <zlib.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <stdarg.h>
@@ -650,22 +649,24 @@ int yb_init_file(yb_ctx *c, const char *path) {
     int rc = YB_OK;
     const size_t map_size = size;
     std::vector<char> inflated;
-    if (size >= 2 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b) {
-        // util.rs:57-72 (niffler sniffs the magic number): gzip input is inflated into memory, then parsed like a plain file
-        gzFile g = gzopen(path, "rb");
-        if (!g) rc = c->fail(YB_ERR_CANT_READ_FILE, "Can't open file %s: %s", path, strerror(errno));
+    const bool packed = (size >= 2 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b) ||
+                        (size >= 3 && !memcmp(data, "BZh", 3)) || (size >= 6 && !memcmp(data, "\xfd" "7zXZ\0", 6));
+    if (packed) {
+        // util.rs:57-72 (niffler sniffs the magic number): gzip / bzip2 / xz input is inflated into memory, then parsed
+        // like a plain file
+        yb::Codec codec;
+        std::string why;
+        yb::ByteSource *src = yb::open_source(path, &codec, &why);
+        if (!src) rc = c->fail(YB_ERR_CANT_READ_FILE, "%s", why.c_str());
         else {
-            gzbuffer(g, 1u << 20);
             std::vector<char> buf(1u << 22);
-            int got;
-            while ((got = gzread(g, buf.data(), (unsigned)buf.size())) > 0) inflated.insert(inflated.end(), buf.data(), buf.data() + got);
-            if (got < 0) rc = c->fail(YB_ERR_CANT_READ_FILE, "Error in compression detection of file %s: corrupt gzip stream", path);
-            gzclose(g);
+            long got;
+            while ((got = src->read(buf.data(), buf.size())) > 0) inflated.insert(inflated.end(), buf.data(), buf.data() + got);
+            if (got < 0) rc = c->fail(YB_ERR_CANT_READ_FILE, "Error in compression detection of file %s: corrupt compressed stream", path);
+            delete src;
             data = inflated.data();
             size = inflated.size();
         }
-    } else if ((size >= 3 && !memcmp(data, "BZh", 3)) || (size >= 6 && !memcmp(data, "\xfd" "7zXZ\0", 6))) {
-        rc = c->fail(YB_ERR_CANT_READ_FILE, "%s is bzip2- or xz-compressed; only gzip is read by this build", path);
     }
     if (rc == YB_OK) {
         rc = yb_init_buffer(c, data, size, t);

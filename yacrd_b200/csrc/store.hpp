@@ -145,6 +145,22 @@ typedef bool (*CsrAllocFn)(void *sink, size_t n_reads, size_t n_iv, uint32_t **r
 bool ingest_buffer_parallel(const char *text, size_t n, int format, int threads, CsrAllocFn alloc, void *sink, BulkIds *ids,
                             IngestError *err);
 
+// codec.cpp: compressed files (util.rs:57-87). open_source sniffs the magic number; open_sink writes `codec` at level 1.
+enum Codec { kPlain = 0, kGzip = 1, kBzip2 = 2, kXz = 3 };
+class ByteSource {
+  public:
+    virtual ~ByteSource() {}
+    virtual long read(void *buf, size_t n) = 0;  // bytes read, 0 at the end, -1 on a corrupt stream / read error
+};
+class ByteSink {
+  public:
+    virtual ~ByteSink() {}
+    virtual bool write(const void *p, size_t n) = 0;
+    virtual bool close() = 0;  // finishes the stream; false if anything failed
+};
+ByteSource *open_source(const char *path, Codec *codec, std::string *err);
+ByteSink *open_sink(const char *path, Codec codec, std::string *err);
+
 // editors.cpp: runs one post-detection editor (yb_editor) over input_path -> output_path, asking `ctx` for the
 // results through the public ABI. Returns a yb_status; *error gets the message unless the context already has it.
 int run_editor(struct ::yb_ctx *ctx, int op, const char *input_path, const char *output_path, size_t buffer_size, std::string *error);
