@@ -61,6 +61,9 @@ typedef struct yb_opts {
 } yb_opts;
 
 #define YB_FLAG_KEEP_HOST_INTERVALS 1u /* keep arrival-order intervals so yb_overlap() works after upload */
+#define YB_FLAG_LAZY_DEVICE 4u /* yb_create does not touch CUDA: the device (context creation, about half a second) is opened
+                                by the first call that needs it (yb_upload, yb_compute_*, yb_peer_*, yb_init_report*). With
+                                yb_device_warmup on another thread, a driver parses its input while CUDA starts up. */
 #define YB_FLAG_HOST_ONLY 2u /* producer side only (ingestion, interning, CSR freeze, Reads2Ovl queries): no device is
                                 touched; yb_upload / yb_compute_* fail with YB_ERR_CUDA. There is still no CPU pile-up. */
 
@@ -85,6 +88,8 @@ void yb_destroy(yb_ctx *ctx);
  * (the reference's compute_all_bad_part loops over get_overlaps batches, stack.rs:148-161). */
 int yb_reset(yb_ctx *ctx);
 const char *yb_last_error(const yb_ctx *ctx);
+/* First CUDA call of the process for `device` (< 0: the current one): safe from any thread, any number of times. */
+int yb_device_warmup(int device);
 const char *yb_version(void);
 const char *yb_type_name(int read_type); /* ReadType::as_str, editor/mod.rs:51-58 */
 

@@ -343,6 +343,24 @@ def test_sharded_equals_unsharded():
     assert np.array_equal(ybd.global_classes(gathered, n, G), want)
 
 
+def test_lazy_device_context():
+    """YB_FLAG_LAZY_DEVICE: yb_create does not touch CUDA; the first call that needs the device opens it (the driver
+    parses its input while yb_device_warmup starts CUDA on another thread)."""
+    from yacrd_b200 import _native as N
+    assert N.lib().yb_device_warmup(-1) == N.OK
+    fm = yb.FullMemory(lazy_device=True)
+    fm.init(os.path.join(GOLDEN, "c1_overlaps.paf"))
+    assert fm.n_reads() == 230
+    bp = yb.FromOverlap(fm, 0, 0.8)
+    bp.compute_all_bad_part()
+    assert sorted(bp.report_lines()) == read_sorted_lines(os.path.join(GOLDEN, "c1_truth.sorted.yacrd"))
+    fm.close()
+    yb.FullMemory(lazy_device=True).close()  # never opened its device: nothing to release
+    rp = yb.FromReport(os.path.join(GOLDEN, "c1_truth.sorted.yacrd"))
+    rp.compute_all_bad_part()
+    rp.ctx.close()
+
+
 def test_reset_reuses_the_context_for_the_next_batch():
     fm = yb.FullMemory()
     for seed in (1, 2):

@@ -20,7 +20,7 @@ ERR_NAMES = {
 }
 NOT_BAD, CHIMERIC, NOT_COVERED = 0, 1, 2
 EDIT_SCRUBB, EDIT_FILTER, EDIT_EXTRACT, EDIT_SPLIT = 0, 1, 2, 3  # yb_editor
-FLAG_KEEP_HOST_INTERVALS, FLAG_HOST_ONLY = 1, 2
+FLAG_KEEP_HOST_INTERVALS, FLAG_HOST_ONLY, FLAG_LAZY_DEVICE = 1, 2, 4
 SYNTH_ONT, SYNTH_PACBIO_SKEW = 0, 1
 
 
@@ -73,6 +73,7 @@ SIGNATURES = {
     "yb_get_bad_part_at": (C.c_int, [_vp, C.c_uint32, C.POINTER(_u32p), _u32p, _u64p, _u8p]),
     "yb_write_report": (C.c_int, [_vp, _cp]),
     "yb_edit": (C.c_int, [_vp, C.c_int, _cp, _cp]),
+    "yb_device_warmup": (C.c_int, [C.c_int]),
     "yb_format_report_line": (C.c_int64, [_vp, C.c_uint32, _vp, _sz]),
     "yb_classes": (_vp, [_vp, C.POINTER(_sz)]),
     "yb_class_bitmap": (_vp, [_vp, C.POINTER(_sz)]),

@@ -198,9 +198,9 @@ def synth_csr(n_reads, mean_intervals, profile=N.SYNTH_ONT, seed=20261017, shard
 class FullMemory(Context):
     """reads2ovl::FullMemory (fullmemory.rs:29-99) + trait Reads2Ovl (reads2ovl/mod.rs:43-163)."""
 
-    def __init__(self, read_buffer_size=8192, device=-1, ingest_threads=0, host_only=False):
+    def __init__(self, read_buffer_size=8192, device=-1, ingest_threads=0, host_only=False, lazy_device=False):
         super().__init__(device=device, read_buffer_size=read_buffer_size, ingest_threads=ingest_threads,
-                         flags=N.FLAG_HOST_ONLY if host_only else 0)
+                         flags=(N.FLAG_HOST_ONLY if host_only else 0) | (N.FLAG_LAZY_DEVICE if lazy_device else 0))
 
     def init(self, filename):  # mod.rs:44-81
         self._ck(self._L.yb_init_file(self._h, _b(filename)))

@@ -13,6 +13,7 @@
 
 #include <chrono>
 #include <string>
+#include <thread>
 
 #include "../../include/yacrd_b200.h"
 
@@ -147,6 +148,14 @@ int main(int argc, char **argv) {
     opts.device = device;
     opts.read_buffer_size = (uint32_t)buffer_size;
     opts.ingest_threads = (uint32_t)threads;
+    opts.flags = YB_FLAG_LAZY_DEVICE;  // CUDA starts up on another thread while the input is parsed
+    std::thread warm([device] { yb_device_warmup(device); });
+    struct Joiner {
+        std::thread &t;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+        }
+    } joiner{warm};
     yb_ctx *ctx = yb_create(&opts);
     if (!ctx) {
         fprintf(stderr, "Error: %s\n", yb_create_error());

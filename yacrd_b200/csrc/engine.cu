@@ -283,6 +283,54 @@ const char *yb_type_name(int t) { return (t >= 0 && t < 3) ? kTypeNames[t] : "?"
 const char *yb_create_error(void) { return g_create_error.c_str(); }
 const char *yb_last_error(const yb_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 
+// Opens the context's device (first CUDA call of the process: context creation, about half a second), its stream and the
+// side stream. yb_create does it unless YB_FLAG_LAZY_DEVICE asks to leave it to the first call that needs the device.
+static int open_device(yb_ctx *c) {
+    if (c->stream) return YB_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return c->fail(YB_ERR_CUDA, "no usable CUDA device (the detect path has no CPU fallback): %s",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    int dev = c->device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    }
+    if (dev >= count || cudaSetDevice(dev) != cudaSuccess) {
+        cudaGetLastError();
+        return c->fail(YB_ERR_CUDA, "invalid CUDA device ordinal %d", dev);
+    }
+    c->device = dev;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        cudaGetLastError();
+        c->stream = nullptr;
+        return c->fail(YB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    // optional: without them the tiers simply run one after the other
+    if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (c->side_stream) cudaStreamDestroy(c->side_stream);
+        c->side_stream = nullptr;
+    }
+    return YB_OK;
+}
+#define YB_DEVICE(ctx)                                   \
+    do {                                                 \
+        if (int rc_ = open_device(ctx)) return rc_;      \
+    } while (0)
+
+int yb_device_warmup(int device) {
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        return YB_ERR_CUDA;
+    }
+    return cudaFree(nullptr) == cudaSuccess ? YB_OK : YB_ERR_CUDA;
+}
+
 yb_ctx *yb_create(const yb_opts *opts) {
     if (opts && (opts->flags & YB_FLAG_HOST_ONLY)) {  // producer side only: no device, no compute
         yb_ctx *c = new (std::nothrow) yb_ctx();
@@ -298,48 +346,22 @@ yb_ctx *yb_create(const yb_opts *opts) {
         c->h_rowptr.plain = c->h_len.plain = c->h_iv.plain = true;
         return c;
     }
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        cudaGetLastError();
-        g_create_error = std::string("no usable CUDA device (the detect path has no CPU fallback): ") +
-                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-        return nullptr;
-    }
     yb_ctx *c = new (std::nothrow) yb_ctx();
     if (!c) {
         g_create_error = "out of memory";
         return nullptr;
     }
-    int dev = opts ? opts->device : -1;
-    if (dev < 0) {
-        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
-    }
-    if (dev >= count || cudaSetDevice(dev) != cudaSuccess) {
-        cudaGetLastError();
-        g_create_error = "invalid CUDA device ordinal " + std::to_string(dev);
-        delete c;
-        return nullptr;
-    }
-    c->device = dev;
+    c->device = opts ? opts->device : -1;
     if (opts) {
         if (opts->read_buffer_size) c->read_buffer_size = opts->read_buffer_size;
         c->flags = opts->flags;
         c->ingest_threads = opts->ingest_threads;
     }
-    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
-        cudaGetLastError();
-        g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+    if (opts && (opts->flags & YB_FLAG_LAZY_DEVICE)) return c;  // the device is opened by the first call that needs it
+    if (open_device(c) != YB_OK) {
+        g_create_error = c->error;
         delete c;
         return nullptr;
-    }
-    // optional: without them the tiers simply run one after the other
-    if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        cudaGetLastError();
-        if (c->side_stream) cudaStreamDestroy(c->side_stream);
-        c->side_stream = nullptr;
     }
     return c;
 }
@@ -353,8 +375,8 @@ void yb_destroy(yb_ctx *c) {
         delete c;
         return;
     }
-    cudaSetDevice(c->device);
-    if (c->stream) {
+    if (c->stream) {  // (a lazy context that never needed its device has nothing to release there)
+        cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
     }
@@ -395,7 +417,7 @@ static std::unordered_set<void *> g_host_plain;
 // (stack.rs:148-161 loops over batches) reuses them.
 int yb_reset(yb_ctx *c) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
-    if (!c->host_only) {
+    if (!c->host_only && c->stream) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
     }
@@ -759,6 +781,7 @@ int yb_upload(yb_ctx *c) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
     if (c->host_only) return c->fail(YB_ERR_CUDA, "host-only context: the detect path runs on a CUDA device only");
     if (c->from_report) return c->fail(YB_ERR_STATE, "context was loaded from a report; nothing to upload");
+    YB_DEVICE(c);
     YB_CUDA(c, cudaSetDevice(c->device));
     if (int rc = freeze(c)) return rc;
     if (c->uploaded) return YB_OK;
@@ -834,6 +857,7 @@ int yb_upload(yb_ctx *c) {
 int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *stream) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
     if (c->host_only) return c->fail(YB_ERR_CUDA, "host-only context: the detect path runs on a CUDA device only");
+    YB_DEVICE(c);
     YB_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     c->coverage = coverage;
@@ -859,6 +883,7 @@ int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *s
 int yb_synchronize(yb_ctx *c) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
     if (c->host_only) return YB_OK;
+    YB_DEVICE(c);
     YB_CUDA(c, cudaSetDevice(c->device));
     YB_CUDA(c, cudaStreamSynchronize(c->stream));
     return YB_OK;
@@ -868,6 +893,7 @@ int yb_download(yb_ctx *c) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
     if (!c->computed) return c->fail(YB_ERR_STATE, "yb_download before yb_compute_device");
     if (c->downloaded) return YB_OK;
+    YB_DEVICE(c);
     YB_CUDA(c, cudaSetDevice(c->device));
     const size_t n = c->n_reads;
     if (!c->h_cls.reserve(n + 1) || !c->h_gap_ptr.reserve(n + 1) || !c->h_bitmap.reserve(c->bitmap_bytes() + 4) ||
@@ -934,7 +960,7 @@ int yb_bind_device_bitmap(yb_ctx *c, void *device_ptr, size_t n_bytes) {
 void *yb_peer_alloc(yb_ctx *c, size_t n_bytes, void *handle_out) {
     if (!c || c->host_only || !handle_out || n_bytes == 0) return nullptr;
     static_assert(sizeof(cudaIpcMemHandle_t) == YB_IPC_HANDLE_BYTES, "handle size");
-    if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+    if (open_device(c) != YB_OK || cudaSetDevice(c->device) != cudaSuccess) return nullptr;
     void *p = nullptr;
     cudaIpcMemHandle_t h;
     if (cudaMalloc(&p, n_bytes) != cudaSuccess || cudaMemset(p, 0, n_bytes) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
@@ -948,7 +974,7 @@ void *yb_peer_alloc(yb_ctx *c, size_t n_bytes, void *handle_out) {
 
 void *yb_peer_open(yb_ctx *c, const void *handle) {
     if (!c || c->host_only || !handle) return nullptr;
-    if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+    if (open_device(c) != YB_OK || cudaSetDevice(c->device) != cudaSuccess) return nullptr;
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, sizeof h);
     void *p = nullptr;
@@ -961,6 +987,7 @@ void *yb_peer_open(yb_ctx *c, const void *handle) {
 
 int yb_peer_close(yb_ctx *c, void *mapped) {
     if (!c || !mapped) return YB_ERR_INVALID_ARGUMENT;
+    YB_DEVICE(c);
     YB_CUDA(c, cudaSetDevice(c->device));
     YB_CUDA(c, cudaStreamSynchronize(c->stream));
     YB_CUDA(c, cudaIpcCloseMemHandle(mapped));
@@ -969,6 +996,7 @@ int yb_peer_close(yb_ctx *c, void *mapped) {
 
 int yb_peer_free(yb_ctx *c, void *allocated) {
     if (!c || !allocated) return YB_ERR_INVALID_ARGUMENT;
+    YB_DEVICE(c);
     YB_CUDA(c, cudaSetDevice(c->device));
     YB_CUDA(c, cudaStreamSynchronize(c->stream));
     YB_CUDA(c, cudaFree(allocated));
@@ -1014,7 +1042,7 @@ void *yb_device_gaps(yb_ctx *c, size_t *cap) {
     if (cap) *cap = c->d_gaps.cap;
     return c->d_gaps.p;
 }
-void *yb_stream(yb_ctx *c) { return c ? c->stream : nullptr; }
+void *yb_stream(yb_ctx *c) { return c && open_device(c) == YB_OK ? c->stream : nullptr; }
 
 int yb_get_stats(yb_ctx *c, yb_stats *out) {
     if (!c || !out) return YB_ERR_INVALID_ARGUMENT;
@@ -1161,6 +1189,7 @@ int yb_init_report_buffer(yb_ctx *c, const char *text, size_t n_bytes) {
     if (!c || (!text && n_bytes)) return YB_ERR_INVALID_ARGUMENT;
     if (c->host_only) return c->fail(YB_ERR_CUDA, "host-only context: reports are classified on a CUDA device only");
     if (c->total_reads() || c->from_report) return c->fail(YB_ERR_STATE, "yb_init_report needs an empty context");
+    YB_DEVICE(c);
     YB_CUDA(c, cudaSetDevice(c->device));
     std::vector<uint32_t> gp(1, 0);
     std::vector<uint2> gaps;
