@@ -40,7 +40,8 @@ typedef enum yb_status {
     YB_ERR_READING = -5,               /* error.rs: ReadingErrorNoFilename (record does not deserialize) */
     YB_ERR_WRITING = -6,               /* error.rs: WritingErrorNoFilename */
     YB_ERR_CORRUPT_REPORT = -7,        /* error.rs: CorruptYacrdReport */
-    YB_ERR_MALFORMED_INTERVAL = -8,    /* new: begin >= end or end > length (SURVEY.md §7 "Malformed input") */
+    YB_ERR_MALFORMED_INTERVAL = -8,    /* reserved (round 1 rejected begin >= end / end > length; such rows are now computed
+                                          with the reference's own heap sweep, see yb_stats.n_malformed_intervals) */
     YB_ERR_INVALID_ARGUMENT = -9,
     YB_ERR_STATE = -10,                /* call order violated (e.g. results queried before compute) */
     YB_ERR_TOO_LARGE = -11,            /* > 2^32-16 intervals or reads in one context, or a read longer than 2^31-1 */
@@ -76,6 +77,9 @@ typedef struct yb_stats {
     uint64_t n_reads_warp, n_reads_cta, n_reads_huge; /* kernel tier each read took */
     uint64_t kernel_launches; /* cumulative count of this library's kernel launches */
     uint64_t h2d_bytes, d2h_bytes; /* cumulative */
+    uint64_t n_malformed_intervals; /* intervals with begin >= end or end > length in the last batch: accepted, like the
+                                       reference does (stack.rs:61-139 has no such test) */
+    uint64_t n_literal_reads;       /* reads holding one: computed by the literal heap sweep kernel, not the closed form */
 } yb_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -170,11 +174,15 @@ int yb_init_report_buffer(yb_ctx *ctx, const char *text, size_t n_bytes);
 /* ---- staged device API (what yb_compute_all_bad_part is made of) ---------------------------- */
 /* Freeze the host store into a CSR (flat (begin,end) buffer + row pointers + lengths) and copy it to HBM;
  * then, once per uploaded CSR and on the device: row statistics, the test 0 <= begin < end <= length of
- * every interval (its count is reported by yb_download as YB_ERR_MALFORMED_INTERVAL) and the size-class
- * worklist of the rows (16 bytes per read). This is the get_overlaps boundary (stack.rs:149). */
+ * every interval (a read that fails it is computed by the reference's own heap sweep, stack.rs:61-139, instead
+ * of the closed form; counts in yb_stats) and the size-class worklist of the rows (16 bytes per read). This is
+ * the get_overlaps boundary (stack.rs:149). */
 int yb_upload(yb_ctx *ctx);
 /* Kernels only; inputs and outputs stay resident in HBM. `stream` is a cudaStream_t (NULL = the
- * context's own stream); the call is asynchronous with respect to the host. */
+ * context's own stream); the call is asynchronous with respect to the host (the first call after a
+ * yb_upload waits for the upload's validation result, 4 bytes). On a caller's stream the step is ordered
+ * behind the upload and yb_download behind the step by events; while that stream is being captured into
+ * a CUDA graph the events are left out and the caller synchronises around capture and replays. */
 int yb_compute_device(yb_ctx *ctx, uint64_t coverage, double not_coverage, void *stream);
 /* D2H of classes, bitmap, gap offsets and gaps (synchronises the stream). */
 int yb_download(yb_ctx *ctx);
@@ -188,11 +196,12 @@ void *yb_stream(yb_ctx *ctx); /* the context's cudaStream_t */
 
 /* ---- peer-memory all-gather of the class bitmap (one process per GPU, same node, NVLink / NVSwitch) -------
  * Instead of a separate collective after the kernels, the ordering kernel stores every word of this rank's 2-bit
- * bitmap straight into slot `rank` of EVERY rank's gather buffer ([n_ranks x slot_bytes], peer stores over NVLink),
- * and a one-CTA kernel closes the step with a flag barrier (release / acquire at system scope), so that when the
- * stream reaches the end of yb_compute_device every rank holds every rank's bitmap. Buffers are plain cudaMalloc
- * allocations shared through CUDA IPC handles, which the caller exchanges with whatever it has (torch.distributed,
- * MPI, a file). */
+ * bitmap straight into slot `rank` of EVERY rank's gather buffer (peer stores over NVLink) and, when its last CTA is
+ * done, releases one flag per peer (system scope). Nothing in a step waits for the slowest rank: the gather buffer is
+ * [2 x n_ranks x slot_bytes] - step s uses half s & 1 - and a rank starts storing step s only once every peer has
+ * finished step s - 1, i.e. (stream order) whatever it read from the half that step s overwrites. The consumer of a
+ * step's bitmaps calls yb_peer_wait on its stream first. Buffers are plain cudaMalloc allocations shared through
+ * CUDA IPC handles, which the caller exchanges with whatever it has (torch.distributed, MPI, a file). */
 #define YB_IPC_HANDLE_BYTES 64
 #define YB_MAX_PEERS 16
 /* Device buffer (zero-filled) that other processes can map; handle_out receives YB_IPC_HANDLE_BYTES bytes. */
@@ -201,15 +210,22 @@ void *yb_peer_alloc(yb_ctx *ctx, size_t n_bytes, void *handle_out);
 void *yb_peer_open(yb_ctx *ctx, const void *handle);
 int yb_peer_close(yb_ctx *ctx, void *mapped);
 int yb_peer_free(yb_ctx *ctx, void *allocated);
-/* gather_bufs[p] / flag_bufs[p]: rank p's gather buffer (n_ranks x slot_bytes bytes) and flag buffer (128 bytes,
- * zero-filled), as mapped in THIS process (own buffers for p == rank). Every rank must run the same number of
- * detect steps (the barrier counts them). n_ranks == 0 unbinds. */
+/* gather_bufs[p] / flag_bufs[p]: rank p's gather buffer (2 x n_ranks x slot_bytes bytes) and flag buffer (128 bytes,
+ * zero-filled; word q = steps rank q has finished, word 31 = steps this rank has finished), as mapped in THIS process
+ * (own buffers for p == rank). Every rank must run the same number of detect steps. n_ranks == 0 unbinds. */
 int yb_bind_peers(yb_ctx *ctx, void *const *gather_bufs, void *const *flag_bufs, uint32_t n_ranks, uint32_t rank,
                   size_t slot_bytes);
+/* Enqueues on `stream` (NULL = the context's) a wait until every rank's slot of this rank's last finished step is
+ * complete in this rank's gather buffer (half (steps - 1) & 1). Bounded: a rank that never arrives is reported by the
+ * next yb_download as YB_ERR_STATE instead of hanging the GPU. */
+int yb_peer_wait(yb_ctx *ctx, void *stream);
 void *yb_device_classes(yb_ctx *ctx, size_t *n);
 void *yb_device_gap_ptr(yb_ctx *ctx, size_t *n);
 void *yb_device_gaps(yb_ctx *ctx, size_t *n_pairs_capacity);
 int yb_get_stats(yb_ctx *ctx, yb_stats *out);
+/* Measurement aid: runs the once-per-upload kernels (row statistics, interval validation, size-class worklist) again on
+ * the resident CSR and returns their device time (CUDA events) in milliseconds. Results of an earlier step are dropped. */
+int yb_time_upload_kernels(yb_ctx *ctx, float *ms_out);
 
 /* ---- synthetic workload generator (BASELINE.json configs). Host only. ---------- */
 typedef struct yb_synth_spec {

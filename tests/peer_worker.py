@@ -15,7 +15,9 @@ def main():
     import yacrd_b200 as yb
     from yacrd_b200 import dist as ybd
     from oracle import yacrd_oracle as o
-    dev = rank % torch.cuda.device_count()
+    ndev = torch.cuda.device_count()
+    dev = rank % ndev
+    print("rank %d: device %d of %d visible (%s)" % (rank, dev, ndev, "one GPU per rank" if ndev >= world else "ranks share a GPU"))
     torch.cuda.set_device(dev)
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % port, rank=rank, world_size=world)
     _, _, counts = ybd.shard_layout(n, world)
@@ -26,15 +28,17 @@ def main():
     pg = ybd.PeerGather(fm, slot)
     full = yb.synth_csr(n, 40)
     want, _, _ = o.run_csr(full.rowptr, full.iv, full.length, 4, 0.4)
-    for it in range(3):  # several steps: the epoch counter must keep the ranks in lock step
-        fm.upload()
+    for it in range(5):  # several steps: the two halves of the gather buffer alternate, no host barrier in between
+        if it < 2:
+            fm.upload()
         fm.compute_device(4, 0.4)
+        pg.wait()
         fm.synchronize()
-        got = pg.tensor().cpu().numpy()
+        got = pg.current().cpu().numpy()
         assert np.array_equal(ybd.global_classes(got, n, world), want), "rank %d step %d: gathered classes differ" % (rank, it)
-        dist.barrier()
     fm.download()
     assert np.array_equal(fm.class_bitmap(), got[rank][: len(fm.class_bitmap())])
+    dist.barrier()
     pg.close()
     fm.close()
     dist.destroy_process_group()

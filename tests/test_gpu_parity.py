@@ -171,14 +171,15 @@ def test_corrupt_report_is_an_error():
     assert e.value.kind == "CorruptYacrdReport"
 
 
-def test_malformed_interval_is_reported_not_fixed():
-    for iv, ln in (((50, 50), 100), ((60, 40), 100), ((10, 120), 100)):
-        fm = yb.FullMemory()
-        fm.add_overlap_and_length("a", iv, ln)
-        with pytest.raises(yb.YacrdError) as e:
-            yb.FromOverlap(fm, 0).compute_all_bad_part()
-        assert e.value.kind == "MalformedInterval"
-        fm.close()
+def test_malformed_intervals_follow_the_reference_kats():
+    """begin >= end or end > length: the reference has no such test and its heap sweep gives a definite answer
+    (stack.rs:61-139); those reads take literal_kernel. One read each, against the oracle's literal sweep."""
+    for ivs, ln in (([(50, 50)], 100), ([(60, 40)], 100), ([(10, 120)], 100), ([(0, 30), (20, 10), (25, 200)], 100),
+                    ([(5, 5), (5, 5), (90, 100)], 100)):
+        for c in (0, 1):
+            gaps, length, _, line = _one_read(ivs, ln, c)
+            want = o.compute_bad_part(ivs, ln, c)
+            assert gaps == want and length == ln, (ivs, ln, c, gaps, want)
 
 
 def _random_csr(rng, n_reads, k_choices, len_choices):
@@ -212,25 +213,69 @@ def test_fuzz_small_reads_every_register_tier(c):
         assert_same_as_oracle(rowptr, iv, length, c, n)
 
 
-@pytest.mark.parametrize("rl_max", [0, 64, 128])
-@pytest.mark.parametrize("c", [0, 1, 3, 4, 7, 8, 30, 63, 64, 127, 5000, 2**32 - 1])
-def test_row_per_lane_tier_every_slot_class_boundary(c, rl_max, monkeypatch):
-    """Rows of every k in 0..140 through the opt-in row-per-lane tier (YB_RL_MAX_SLOTS: packed rows with
-    k + min(c, k) + 1 <= rl_max key slots, in slot classes of 8) and through the default lane-group tier (rl_max = 0):
-    every class boundary, the hand-over between the tiers, short and 16-bit-limit lengths."""
-    monkeypatch.setenv("YB_RL_MAX_SLOTS", str(rl_max))
+@pytest.mark.parametrize("c", [0, 1, 3, 4, 7, 8, 15, 16, 17, 30, 63, 64, 127, 5000, 2**32 - 1])
+def test_every_k_up_to_530_and_every_class_boundary(c):
+    """Rows of every k in 0..530 (every size class of the register tier: 16, 32, 48, 64, 80, 96, 128, 160, 256, 512 key
+    slots, both ends of each, and the hand-over to the CTA tier), short and 16-bit-limit lengths, behind random rows."""
     rng = random.Random(4242 + c % 1000)
     rowptr, iv, length = _random_csr(rng, 141 * 40, list(range(141)), [1, 5, 40, 3000, 65534, 65535])
-    # every k really occurs at least once, in this order, behind the random rows
-    rp2, iv2, len2 = _random_csr(random.Random(7), 141, [0], [1000])
-    rows = [[(rng.randrange(0, 900), 1000 - rng.randrange(0, 90)) for _ in range(k)] for k in range(141)]
-    rp2 = np.zeros(142, dtype=np.uint32)
+    rows = [[(rng.randrange(0, 900), 1000 - rng.randrange(0, 90)) for _ in range(k)] for k in range(531)]
+    rp2 = np.zeros(532, dtype=np.uint32)
     rp2[1:] = np.cumsum([len(r) for r in rows])
     iv2 = np.array([p for r in rows for p in r], dtype=np.uint32).reshape(-1, 2)
     rowptr = np.concatenate([rowptr, rowptr[-1] + rp2[1:]]).astype(np.uint32)
     iv = np.concatenate([iv, iv2])
-    length = np.concatenate([length, len2]).astype(np.uint32)
+    length = np.concatenate([length, np.full(531, 1000)]).astype(np.uint32)
     assert_same_as_oracle(rowptr, iv, length, c, 0.4)
+
+
+def _malformed_csr(rng, n_reads, k_choices, len_choices, p_bad_row):
+    rowptr, iv, length = _random_csr(rng, n_reads, k_choices, len_choices)
+    iv = iv.copy()
+    bad_rows = 0
+    for r in range(n_reads):
+        k = int(rowptr[r + 1] - rowptr[r])
+        if k == 0 or rng.random() >= p_bad_row:
+            continue
+        bad_rows += 1
+        for _ in range(rng.choice([1, 1, 2, k])):
+            i = int(rowptr[r]) + rng.randrange(k)
+            kind = rng.randrange(4)
+            ln = int(length[r])
+            if kind == 0:
+                iv[i] = (iv[i][0], iv[i][0])                       # empty
+            elif kind == 1:
+                iv[i] = (iv[i][1], iv[i][0])                       # reversed
+            elif kind == 2:
+                iv[i] = (iv[i][0], ln + rng.randrange(1, 70000))   # beyond the read's end
+            else:
+                iv[i] = (rng.randrange(0, 2**32), rng.randrange(0, 2**32))
+    return rowptr, iv, length, bad_rows
+
+
+@pytest.mark.parametrize("c", [0, 2, 4])
+def test_fuzz_malformed_rows_take_the_literal_sweep(c):
+    """3 % of the rows (every size class, the CTA tier included) get empty / reversed / out-of-range / random intervals:
+    the whole batch still equals the oracle's literal heap sweep, and the stats say how many rows took literal_kernel."""
+    rng = random.Random(99 + c)
+    rowptr, iv, length, bad_rows = _malformed_csr(rng, 8000, [0, 1, 2, 5, 16, 17, 40, 64, 65, 100, 200, 513, 700],
+                                                  [1, 50, 3000, 65534, 65535, 250000], 0.03)
+    fm = yb.FullMemory()
+    fm.add_csr(rowptr, iv, length)
+    bp = yb.FromOverlap(fm, c, 0.4)
+    bp.compute_all_bad_part()
+    gp, gaps = bp.gap_csr()
+    w_cls, w_gp, w_gaps = o.run_csr(rowptr, iv, length, c, 0.4)
+    assert np.array_equal(gp.astype(np.uint64), w_gp) and np.array_equal(gaps, w_gaps) and np.array_equal(bp.classes(), w_cls)
+    st = fm.stats()
+    assert 0 < st["n_literal_reads"] <= bad_rows and st["n_malformed_intervals"] >= st["n_literal_reads"]
+    fm.close()
+
+
+def test_all_rows_malformed():
+    rng = random.Random(5150)
+    rowptr, iv, length, _ = _malformed_csr(rng, 3000, [1, 3, 20, 70, 600], [100, 70000], 1.0)
+    assert_same_as_oracle(rowptr, iv, length, 1, 0.4)
 
 
 def test_fuzz_tiny_positions_many_ties():
@@ -262,21 +307,6 @@ def test_empty_context_and_reads_without_intervals():
     iv = np.array([[5, 9]], dtype=np.uint32)
     length = np.array([100, 0, 10, 7], dtype=np.uint32)
     assert_same_as_oracle(rowptr, iv, length, 0, 0.8)
-
-
-@pytest.mark.parametrize("rl_max", [64, 128])
-def test_row_per_lane_tier_synthetic_and_golden(rl_max, monkeypatch, tmp_path):
-    """The opt-in row-per-lane tier on the golden PAF and on a synthetic shard, bit-exact like the default tier."""
-    monkeypatch.setenv("YB_RL_MAX_SLOTS", str(rl_max))
-    fm = yb.FullMemory()
-    fm.init(os.path.join(GOLDEN, "c1_overlaps.paf"))
-    bp = yb.FromOverlap(fm, 0, 0.8)
-    bp.compute_all_bad_part()
-    assert sorted(bp.report_lines()) == read_sorted_lines(os.path.join(GOLDEN, "c1_truth.sorted.yacrd"))
-    fm.close()
-    csr = yb.synth_csr(60000, 50)
-    for c, n in ((4, 0.4), (0, 0.8)):
-        assert_same_as_oracle(csr.rowptr, csr.iv, csr.length, c, n)
 
 
 def test_config2_100k_reads_c0():

@@ -56,6 +56,7 @@ def srcline(loc):
     return L[n - 1].strip()[:100] if 0 < n <= len(L) else f
 print("total warp-inst %.4g  samples %.4g  smem-excess-wavefronts %.4g" % tuple(tot))
 print(" inst%  smpl%  bankx%  line  source")
-for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+key_ix = 1 if os.environ.get("BY_SAMPLES") else 0
+for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][key_ix])[:top]:
     print("%5.1f  %5.1f  %5.1f  %5s  %s" % (100 * a[0] / tot[0], 100 * a[1] / max(tot[1], 1), 100 * a[2] / max(tot[2], 1),
                                           loc[1] if loc else "?", srcline(loc)))

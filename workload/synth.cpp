@@ -1,4 +1,7 @@
-// synth.cpp — synthetic overlap workloads for BASELINE.json's configs. Host only.
+// synth.cpp — synthetic overlap workloads for BASELINE.json's configs. Host only, no CUDA.
+// Compiled twice: into the product library (the yb_synth_* entries of include/yacrd_b200.h) and, by workload/Makefile,
+// into workload/libyacrd_synth.so, which bench.py's reference arm and the oracle-side tools load instead, so that the
+// CPU arm never maps the product library.
 //
 // Counter-based: every value of read r is a pure function of (seed, r), so a shard can be generated
 // on its own and any subset of reads reproduces bit for bit. Reads are assigned to shards by
@@ -23,7 +26,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/yacrd_b200.h"
+#include "../include/yacrd_b200.h"
 
 namespace {
 

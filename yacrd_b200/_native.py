@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyacrd_b200.so")
+# YB_LIB_PATH: a development knob (A/B runs of differently compiled kernels); the product is the in-tree library
+LIB_PATH = os.environ.get("YB_LIB_PATH") or os.path.join(_HERE, "libyacrd_b200.so")
 
 OK = 0
 ERR_NAMES = {
@@ -33,7 +34,7 @@ class YbStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_reads", "n_intervals", "n_gaps", "n_not_bad", "n_chimeric", "n_not_covered",
         "max_intervals_per_read", "n_reads_warp", "n_reads_cta", "n_reads_huge", "kernel_launches",
-        "h2d_bytes", "d2h_bytes")]
+        "h2d_bytes", "d2h_bytes", "n_malformed_intervals", "n_literal_reads")]
 
 
 class YbSynthSpec(C.Structure):
@@ -100,6 +101,8 @@ SIGNATURES = {
     "yb_peer_close": (C.c_int, [_vp, _vp]),
     "yb_peer_free": (C.c_int, [_vp, _vp]),
     "yb_bind_peers": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _sz]),
+    "yb_peer_wait": (C.c_int, [_vp, _vp]),
+    "yb_time_upload_kernels": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "yb_synth_paf": (C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint64, _vp, C.c_uint64]),
     "yb_synth_fill": (C.c_int, [C.POINTER(YbSynthSpec), _vp, _vp, _vp, C.c_uint32, _vp, C.c_int]),
 }

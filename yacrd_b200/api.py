@@ -99,6 +99,12 @@ class Context:
     def compute_all(self, coverage, not_coverage):
         self._ck(self._L.yb_compute_all_bad_part(self._h, int(coverage), float(not_coverage)))
 
+    def time_upload_kernels(self):
+        """Device milliseconds of the once-per-upload kernels (row statistics, validation, worklist), re-run on the resident CSR."""
+        ms = C.c_float(0)
+        self._ck(self._L.yb_time_upload_kernels(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def stats(self):
         st = N.YbStats()
         self._ck(self._L.yb_get_stats(self._h, C.byref(st)))

@@ -111,7 +111,11 @@ struct yb_ctx {
     uint32_t flags = 0;
     uint32_t ingest_threads = 0;
     bool host_only = false;
-    bool worklist_ready = false;  // the lane-group worklist in d_scratch matches the uploaded CSR
+    cudaEvent_t ev_upload = nullptr;   // last upload work on `stream` (a compute on another stream waits for it)
+    cudaEvent_t ev_compute = nullptr;  // last detect step enqueued on a caller's stream (yb_download waits for it)
+    bool compute_foreign = false;      // ev_compute is pending
+    bool literal_known = false;        // the upload's validation result (rows for the literal heap sweep) has been read
+    uint32_t n_literal = 0, n_malformed = 0;
     bool bulk_frozen = false;  // the CSR came straight from the parallel ingester: `pending` does not hold it
     std::string error;
 
@@ -138,6 +142,7 @@ struct yb_ctx {
     DeviceBuf<uint8_t> d_cls, d_bitmap, d_scratch;
     DeviceBuf<yb::DevRowStats> d_rowstats;
     PinnedBuf<yb::DevRowStats> h_rowstats;
+    PinnedBuf<uint32_t> h_peer_step;
     uint8_t *ext_bitmap = nullptr;  // yb_bind_device_bitmap
     size_t ext_bitmap_bytes = 0;
     // peer-memory all-gather (yb_bind_peers)
@@ -269,7 +274,7 @@ int freeze(yb_ctx *c) {
 int ensure_result_buffers(yb_ctx *c) {
     const size_t n = c->n_reads;
     if (!c->d_cls.reserve(n + 16) || !c->d_gap_ptr.reserve(n + 1) || !c->d_bitmap.reserve(c->bitmap_bytes() + 4) ||
-        !c->d_counters.reserve(yb::kNumCounters) || !c->d_gaps.reserve((size_t)c->n_iv + n + 1))
+        !c->d_counters.reserve(yb::kCounterWords) || !c->d_gaps.reserve((size_t)c->n_iv + n + 1))
         return c->fail(YB_ERR_NOMEM, "device allocation failed (%zu reads, %u intervals)", n, c->n_iv);
     return YB_OK;
 }
@@ -315,6 +320,11 @@ static int open_device(yb_ctx *c) {
         cudaGetLastError();
         if (c->side_stream) cudaStreamDestroy(c->side_stream);
         c->side_stream = nullptr;
+    }
+    if (cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) != cudaSuccess) {
+        e = cudaGetLastError();
+        return c->fail(YB_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
     }
     return YB_OK;
 }
@@ -386,6 +396,9 @@ void yb_destroy(yb_ctx *c) {
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_upload) cudaEventDestroy(c->ev_upload);
+    if (c->ev_compute) cudaEventDestroy(c->ev_compute);
+    c->h_peer_step.release();
     c->h_rowptr.release();
     c->h_len.release();
     c->h_iv.release();
@@ -747,7 +760,7 @@ static int detect_args(yb_ctx *c, yb::DetectArgs *out) {
     a.n_reads = c->n_reads;
     a.n_iv = c->n_iv;
     a.max_k = c->max_k;
-    a.worklist_ready = c->worklist_ready ? 1u : 0u;
+    a.n_literal = c->n_literal;
     a.rows = c->rows;
     a.cls = c->d_cls.p;
     a.gap_ptr = c->d_gap_ptr.p;
@@ -766,6 +779,7 @@ static int detect_args(yb_ctx *c, yb::DetectArgs *out) {
         if (c->peer_slot_bytes < c->bitmap_bytes())
             return c->fail(YB_ERR_INVALID_ARGUMENT, "peer slot too small (%zu < %zu bytes)", c->peer_slot_bytes, c->bitmap_bytes());
         a.rank = c->peer_rank;
+        a.peer_parity_bytes = (size_t)c->n_peers * c->peer_slot_bytes;
         for (uint32_t p = 0; p < c->n_peers; ++p) {
             a.peer_slot[p] = c->peer_gather[p] + (size_t)c->peer_rank * c->peer_slot_bytes;
             a.peer_flag[p] = c->peer_flags[p];
@@ -817,20 +831,14 @@ int yb_upload(yb_ctx *c) {
         rs.huge_keys = ds.huge_keys;
         rs.n_wide = ds.n_wide;
         for (int q = 0; q < yb::kNumClasses; ++q) rs.class_count[q] = ds.class_count[q];
-        for (uint32_t q = 0; q < yb::kRLMaxSlots; ++q) rs.k_hist[q] = ds.k_hist[q];
         c->rows = rs;
         c->max_k = ds.max_k;
     }
-    // 0 <= begin < end <= length is tested once, here, behind the interval copy (the CSR cannot change afterwards);
-    // yb_download reads the count back with the results
-    const int vl = yb::launch_validate(c->d_iv.p, c->d_rowptr.p, c->d_len.p, c->n_reads, c->n_iv, c->d_rowstats.p, c->stream);
-    if (vl < 0) return c->cuda_fail(cudaGetLastError(), "interval validation kernel");
-    c->stats.kernel_launches += (uint64_t)vl;
+    // behind the interval copy, once per CSR (it cannot change afterwards): 0 <= begin < end <= length for every interval
+    // (rows that fail take the literal heap sweep) and the size-class worklist of the register tier
     const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->rows);
     if (!c->d_scratch.reserve(sb)) return c->fail(YB_ERR_NOMEM, "device scratch allocation failed (%zu bytes)", sb);
-    {   // the size-class worklist of the lane-group tier depends on rowptr / len only: built once, here
-        c->worklist_ready = false;
-        if (!c->d_counters.reserve(yb::kNumCounters)) return c->fail(YB_ERR_NOMEM, "device allocation failed");
+    {
         yb::DetectArgs a{};
         a.iv = c->d_iv.p;
         a.rowptr = c->d_rowptr.p;
@@ -842,10 +850,14 @@ int yb_upload(yb_ctx *c) {
         a.counters = c->d_counters.p;
         a.scratch = c->d_scratch.p;
         a.scratch_bytes = c->d_scratch.cap;
-        const int wl = yb::launch_worklist(a, c->stream);
-        if (wl < 0) return c->cuda_fail(cudaGetLastError(), "worklist kernel");
-        c->stats.kernel_launches += (uint64_t)wl;
-        c->worklist_ready = true;
+        const int ul = yb::launch_upload_kernels(a, c->d_rowstats.p, c->stream);
+        if (ul < 0) return c->cuda_fail(cudaGetLastError(), "upload kernels (validation, worklist)");
+        c->stats.kernel_launches += (uint64_t)ul;
+        // the validation result travels back now; yb_compute_device reads it (it decides whether literal_kernel runs)
+        YB_CUDA(c, cudaMemcpyAsync(c->h_rowstats.p, c->d_rowstats.p, sizeof(yb::DevRowStats), cudaMemcpyDeviceToHost, c->stream));
+        YB_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));
+        c->literal_known = false;
+        c->n_literal = c->n_malformed = 0;
     }
     c->stats.h2d_bytes += sizeof(uint32_t) * (2 * n + 1) + sizeof(uint2) * m;
     c->stats.d2h_bytes += sizeof(yb::DevRowStats);
@@ -862,21 +874,83 @@ int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *s
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     c->coverage = coverage;
     c->not_coverage = not_coverage;
+    // a caller's stream: the step must run behind the upload (and a previous download) enqueued on the context's stream,
+    // and yb_download behind the step. While the caller captures a CUDA graph the events stay out of it (the caller
+    // synchronises around capture and replay).
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st != c->stream) cudaStreamIsCapturing(st, &cap);
+    const bool foreign = st != c->stream && cap == cudaStreamCaptureStatusNone;
     int launches;
     if (c->from_report) {
+        if (foreign) {
+            YB_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));
+            YB_CUDA(c, cudaStreamWaitEvent(st, c->ev_upload, 0));
+        }
         launches = yb::launch_classify(c->d_len.p, c->d_gap_ptr.p, c->d_gaps.p, c->n_reads, not_coverage, c->d_cls.p,
                                        c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p, c->d_counters.p, st);
     } else {
         if (!c->uploaded) return c->fail(YB_ERR_STATE, "yb_compute_device before yb_upload");
-        if (yb::rl_max_slots() != 0) c->worklist_ready = false;  // that step rewrites the worklist with its own classes
+        if (!c->literal_known) {  // the validation kernel's verdict (4 bytes that left the device right behind it)
+            YB_CUDA(c, cudaEventSynchronize(c->ev_upload));
+            c->n_literal = c->h_rowstats.p->malformed_rows;
+            c->n_malformed = c->h_rowstats.p->malformed;
+            c->literal_known = true;
+        }
+        if (foreign) {
+            YB_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));  // (also covers a download of the previous step)
+            YB_CUDA(c, cudaStreamWaitEvent(st, c->ev_upload, 0));
+        }
         yb::DetectArgs a{};
         if (int rc = detect_args(c, &a)) return rc;
         launches = yb::launch_detect(a, coverage > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)coverage, not_coverage, st);
     }
     if (launches < 0) return c->cuda_fail(cudaGetLastError(), "kernel launch");
+    if (foreign) {
+        YB_CUDA(c, cudaEventRecord(c->ev_compute, st));
+        c->compute_foreign = true;
+    }
     c->stats.kernel_launches += (uint64_t)launches;
     c->computed = true;
     c->downloaded = false;
+    return YB_OK;
+}
+
+int yb_time_upload_kernels(yb_ctx *c, float *ms_out) {
+    if (!c || !ms_out) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->uploaded || c->from_report) return c->fail(YB_ERR_STATE, "yb_time_upload_kernels needs an uploaded CSR");
+    YB_DEVICE(c);
+    YB_CUDA(c, cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    YB_CUDA(c, cudaEventCreate(&e0));
+    YB_CUDA(c, cudaEventCreate(&e1));
+    yb::DetectArgs a{};
+    int rc = detect_args(c, &a);
+    if (rc == YB_OK) {
+        cudaEventRecord(e0, c->stream);
+        const int l0 = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->stream);
+        const int l1 = yb::launch_upload_kernels(a, c->d_rowstats.p, c->stream);
+        cudaEventRecord(e1, c->stream);
+        if (l0 < 0 || l1 < 0 || cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(ms_out, e0, e1) != cudaSuccess)
+            rc = c->cuda_fail(cudaGetLastError(), "upload kernels");
+        else
+            c->stats.kernel_launches += (uint64_t)(l0 + l1);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->computed = c->downloaded = false;  // the counters were reset with the worklist
+    return rc;
+}
+
+int yb_peer_wait(yb_ctx *c, void *stream) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->n_peers) return YB_OK;
+    YB_DEVICE(c);
+    YB_CUDA(c, cudaSetDevice(c->device));
+    yb::DetectArgs a{};
+    if (int rc = detect_args(c, &a)) return rc;
+    const int l = yb::launch_peer_wait(a, stream ? static_cast<cudaStream_t>(stream) : c->stream);
+    if (l < 0) return c->cuda_fail(cudaGetLastError(), "peer wait kernel");
+    c->stats.kernel_launches += (uint64_t)l;
     return YB_OK;
 }
 
@@ -895,30 +969,43 @@ int yb_download(yb_ctx *c) {
     if (c->downloaded) return YB_OK;
     YB_DEVICE(c);
     YB_CUDA(c, cudaSetDevice(c->device));
+    if (c->compute_foreign) {  // the step ran on a caller's stream: the copies below go behind it
+        YB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_compute, 0));
+        c->compute_foreign = false;
+    }
     const size_t n = c->n_reads;
-    if (!c->h_cls.reserve(n + 1) || !c->h_gap_ptr.reserve(n + 1) || !c->h_bitmap.reserve(c->bitmap_bytes() + 4) ||
-        !c->h_counters.reserve(yb::kNumCounters))
+    const bool peers = c->n_peers && !c->from_report;
+    if (!c->h_cls.reserve(n + 1) || !c->h_gap_ptr.reserve(n + 1) || !c->h_bitmap.reserve(2 * (c->bitmap_bytes() + 4)) ||
+        !c->h_counters.reserve(yb::kCounterWords) || !c->h_peer_step.reserve(1))
         return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
-    YB_CUDA(c, cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, sizeof(uint32_t) * yb::kNumCounters, cudaMemcpyDeviceToHost, c->stream));
+    YB_CUDA(c, cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, sizeof(uint32_t) * yb::kCounterWords, cudaMemcpyDeviceToHost, c->stream));
     YB_CUDA(c, cudaMemcpyAsync(c->h_gap_ptr.p, c->d_gap_ptr.p, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, c->stream));
-    if (!c->from_report)
-        YB_CUDA(c, cudaMemcpyAsync(c->h_rowstats.p, c->d_rowstats.p, sizeof(yb::DevRowStats), cudaMemcpyDeviceToHost, c->stream));
+    const size_t bmb = c->bitmap_bytes();
     if (n) {
         YB_CUDA(c, cudaMemcpyAsync(c->h_cls.p, c->d_cls.p, n, cudaMemcpyDeviceToHost, c->stream));
-        const uint8_t *bm = c->n_peers && !c->from_report ? c->peer_gather[c->peer_rank] + (size_t)c->peer_rank * c->peer_slot_bytes
-                                                         : (c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p);
-        YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p, bm, c->bitmap_bytes(), cudaMemcpyDeviceToHost, c->stream));
+        if (peers) {  // this rank's slot of the last step: even steps use the first half of the gather buffer, odd ones the second
+            const uint8_t *own = c->peer_gather[c->peer_rank] + (size_t)c->peer_rank * c->peer_slot_bytes;
+            YB_CUDA(c, cudaMemcpyAsync(c->h_peer_step.p, c->peer_flags[c->peer_rank] + 31, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p, own, bmb, cudaMemcpyDeviceToHost, c->stream));
+            YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p + bmb + 4, own + (size_t)c->n_peers * c->peer_slot_bytes, bmb, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p, c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p, bmb, cudaMemcpyDeviceToHost, c->stream));
+        }
     }
     YB_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (const uint32_t bad = c->from_report ? 0u : c->h_rowstats.p->malformed)
-        return c->fail(YB_ERR_MALFORMED_INTERVAL,
-                       "%u interval(s) violate 0 <= begin < end <= length; the reference's result is undefined for them", bad);
-    if (c->h_counters.p[yb::kCntPeerTimeout])
-        return c->fail(YB_ERR_STATE, "peer all-gather: %u rank(s) never signalled this step", c->h_counters.p[yb::kCntPeerTimeout]);
-    if (c->h_counters.p[yb::kCntStageOverflow])
-        return c->fail(YB_ERR_STATE, "internal error: bad-region staging buffer overflow (%u reads)", c->h_counters.p[yb::kCntStageOverflow]);
+    if (peers && n && ((*c->h_peer_step.p - 1u) & 1u)) memcpy(c->h_bitmap.p, c->h_bitmap.p + bmb + 4, bmb);
+    // the counter set of the last step: the step number was incremented when the step closed
+    const uint32_t *hc = c->h_counters.p;
+    const uint32_t *set = c->from_report ? hc : hc + ((hc[yb::kCntEpoch] - 1u) & 1u) * yb::kNumCounters;
+    if (!c->from_report && n && hc[yb::kCntEpoch] == 0)
+        return c->fail(YB_ERR_STATE, "internal error: the detect step did not complete");
+    if (set[yb::kCntPeerTimeout] || hc[yb::kCntPeerTimeoutWait])
+        return c->fail(YB_ERR_STATE, "peer all-gather: a rank never signalled its step (%u / %u)", set[yb::kCntPeerTimeout],
+                       hc[yb::kCntPeerTimeoutWait]);
+    if (set[yb::kCntStageOverflow])
+        return c->fail(YB_ERR_STATE, "internal error: bad-region staging buffer overflow (%u reads)", set[yb::kCntStageOverflow]);
     c->n_gaps = c->h_gap_ptr.p[n];
-    size_t d2h = sizeof(uint32_t) * (n + 1 + yb::kNumCounters) + n + c->bitmap_bytes();
+    size_t d2h = sizeof(uint32_t) * (n + 1 + yb::kCounterWords) + n + bmb;
     if (!c->from_report) {
         if (!c->h_gaps.reserve((size_t)c->n_gaps + 1)) return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
         if (c->n_gaps) {
@@ -931,13 +1018,18 @@ int yb_download(yb_ctx *c) {
     c->stats.n_reads = n;
     c->stats.n_intervals = c->n_iv;
     c->stats.n_gaps = c->n_gaps;
-    uint64_t hist[3] = {c->h_counters.p[yb::kCntNotBad], c->h_counters.p[yb::kCntChimeric], c->h_counters.p[yb::kCntNotCovered]};
-    for (uint32_t sl = 0; sl < yb::kHistSlots; ++sl)  // the detect step stripes its histogram over kHistSlots copies
-        for (int t = 0; t < 3; ++t) hist[t] += c->h_counters.p[yb::kCntHist + 3 * sl + t];
+    uint64_t hist[3] = {0, 0, 0};
+    if (n) {
+        for (int t = 0; t < 3; ++t) hist[t] = set[yb::kCntNotBad + t];  // classify_kernel (FromReport path)
+        for (uint32_t sl = 0; sl < yb::kHistSlots; ++sl)  // the detect step stripes its histogram over kHistSlots copies
+            for (int t = 0; t < 3; ++t) hist[t] += set[yb::kCntHist + 3 * sl + t];
+    }
     c->stats.n_not_bad = hist[0];
     c->stats.n_chimeric = hist[1];
     c->stats.n_not_covered = hist[2];
     c->stats.max_intervals_per_read = c->max_k;
+    c->stats.n_malformed_intervals = c->from_report ? 0 : c->n_malformed;
+    c->stats.n_literal_reads = c->from_report ? 0 : c->n_literal;
     c->downloaded = true;
     return YB_OK;
 }
@@ -1284,7 +1376,7 @@ int yb_init_report_buffer(yb_ctx *c, const char *text, size_t n_bytes) {
     c->n_gaps = (uint32_t)at;
     c->from_report = true;
     if (!c->d_len.reserve(n + 1) || !c->d_gap_ptr.reserve(n + 1) || !c->d_gaps.reserve(at + 1) || !c->d_cls.reserve(n + 16) ||
-        !c->d_bitmap.reserve(c->bitmap_bytes() + 4) || !c->d_counters.reserve(yb::kNumCounters))
+        !c->d_bitmap.reserve(c->bitmap_bytes() + 4) || !c->d_counters.reserve(yb::kCounterWords))
         return c->fail(YB_ERR_NOMEM, "device allocation failed");
     YB_CUDA(c, cudaMemcpyAsync(c->d_len.p, c->h_len.p, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
     YB_CUDA(c, cudaMemcpyAsync(c->d_gap_ptr.p, c->h_gap_ptr.p, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, c->stream));

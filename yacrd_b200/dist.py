@@ -85,9 +85,11 @@ def global_classes(gathered, n_reads, n_shards):
 
 class PeerGather:
     """All-gather of the class bitmap fused into the kernels' epilogue over NVLink peer memory (include/yacrd_b200.h,
-    "peer-memory all-gather"): every rank allocates one gather buffer [world x slot_bytes] and one flag buffer, the CUDA
-    IPC handles travel through torch.distributed (any backend), every rank maps every other rank's buffers, and from
-    then on `ctx.compute_device()` leaves all ranks' bitmaps in every rank's buffer — no separate collective."""
+    "peer-memory all-gather"): every rank allocates one gather buffer [2 x world x slot_bytes] (step s uses half s & 1)
+    and one flag buffer, the CUDA IPC handles travel through torch.distributed (any backend), every rank maps every
+    other rank's buffers, and from then on `ctx.compute_device()` leaves all ranks' bitmaps in every rank's buffer - no
+    separate collective and nothing in a step that waits for the slowest rank. A consumer calls `wait()` (a flag wait on
+    the stream) and then reads `current()`."""
 
     def __init__(self, ctx, slot_bytes, group=None):
         import ctypes as C
@@ -99,7 +101,7 @@ class PeerGather:
             raise ValueError("PeerGather supports at most 16 ranks")
         L = ctx._L
         hg, hf = C.create_string_buffer(64), C.create_string_buffer(64)
-        self._own_gather = L.yb_peer_alloc(ctx._h, self.world * self.slot_bytes, hg)
+        self._own_gather = L.yb_peer_alloc(ctx._h, 2 * self.world * self.slot_bytes, hg)
         self._own_flags = L.yb_peer_alloc(ctx._h, 128, hf)
         if not self._own_gather or not self._own_flags:
             raise N.YacrdError(-12, L.yb_last_error(ctx._h).decode())
@@ -123,14 +125,29 @@ class PeerGather:
         ctx._ck(L.yb_bind_peers(ctx._h, ga, fa, self.world, self.rank, self.slot_bytes))
         dist.barrier(group=group)  # nobody starts writing before everybody has mapped
 
-    @property
-    def __cuda_array_interface__(self):
-        return {"shape": (self.world, self.slot_bytes), "typestr": "|u1", "data": (int(self._own_gather), False), "version": 2}
+    class _Arr:
+        def __init__(self, ptr, shape, typestr):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
     def tensor(self):
-        """This rank's gather buffer as a [world, slot_bytes] uint8 torch tensor (a view, no copy)."""
+        """This rank's gather buffer as a [2, world, slot_bytes] uint8 torch tensor (a view, no copy)."""
         import torch
-        return torch.as_tensor(self, device="cuda")
+        return torch.as_tensor(self._Arr(self._own_gather, (2, self.world, self.slot_bytes), "|u1"), device="cuda")
+
+    def flags(self):
+        """This rank's flag words (int32 view): [q] = steps rank q has finished, [31] = steps this rank has finished."""
+        import torch
+        return torch.as_tensor(self._Arr(self._own_flags, (32,), "<i4"), device="cuda")
+
+    def wait(self, stream=None):
+        """Enqueues (on `stream`, a raw cudaStream_t, default the context's) the wait for every rank's slot of this
+        rank's last finished step."""
+        self.ctx._ck(self.ctx._L.yb_peer_wait(self.ctx._h, stream))
+
+    def current(self):
+        """[world, slot_bytes] view of the half the last finished step wrote (synchronises to read the step count)."""
+        steps = int(self.flags()[31].item())
+        return self.tensor()[(steps - 1) & 1]
 
     def close(self):
         L = self.ctx._L
