@@ -80,37 +80,30 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 constexpr int E = 16;                          // keys per lane per array in the register tier
 constexpr uint32_t kSmallMaxK = kRegisterTierMaxK;
 #ifndef YB_SORT_WARPS
-#define YB_SORT_WARPS 1
+#define YB_SORT_WARPS (YB_KE == 32 ? 16 : 24)
 #endif
-constexpr uint32_t kSortWarps = YB_SORT_WARPS;  // warps per CTA of sort_kernel (warps never synchronise with each other)
+constexpr uint32_t kSortWarps = YB_SORT_WARPS;  // warps of sort_kernel's one CTA per SM (they only share the batch counter)
 constexpr uint32_t kSortThreads = kSortWarps * 32;
-#ifndef YB_SORT_MIN_CTAS
-#define YB_SORT_MIN_CTAS (16 / YB_SORT_WARPS)
-#endif
 #ifndef YB_BUF_INTERVALS
-#define YB_BUF_INTERVALS 1088
+#define YB_BUF_INTERVALS (32 * (YB_KE + 2))
 #endif
-constexpr uint32_t kBufIntervals = YB_BUF_INTERVALS;  // row slots of a slab buffer: a batch of class G holds min(floor(32 / G),
-                                                      // floor(kBufIntervals / (32 G + 2))) rows; 1088 = 32 rows of the G = 1 class
+constexpr uint32_t kBufIntervals = YB_BUF_INTERVALS;  // row slots of a warp's slab buffer: a batch of class G holds min(floor(32 / G),
+                                                      // floor(kBufIntervals / (kE G + 2))) rows; 32 (kE + 2) = 32 rows of the G = 1 class
 constexpr uint32_t kScatterRows = 1024;        // rows per CTA of scatter_kernel
 constexpr uint32_t kPartShift = 11, kPartRows = 1u << kPartShift;  // rows per CTA of order_kernel (kOrderThreads x kOrderRows)
 constexpr uint32_t kOrderThreads = 512, kOrderRows = kPartRows / kOrderThreads;
-constexpr uint32_t kStageChunk = 1024;       // pairs a warp reserves in the staging buffer per atomic
+constexpr uint32_t kStageChunk = 2048;       // pairs a warp reserves in the staging buffer per atomic (an L2 round trip the warp waits for)
 constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
 
-// Host-built table of the size classes of ONE sorting kernel (the packed rows or the long reads): kNumG classes, index gi.
+// Host-built table of the size classes (sizes are known from the row pointers at upload time).
 struct ClassTab {
-    uint32_t entry_base[kNumG];     // where the class's records start in the worklist
-    uint32_t count[kNumG];          // rows in the class
-    uint32_t order[kNumG];          // classes in processing order (largest groups first)
-    uint32_t item_base[kNumG + 1];  // batches before the q-th class in processing order
-    uint32_t lanes[kNumG];          // G: lanes per row
-    uint32_t rpb[kNumG];            // rows per batch
-    uint32_t inv[kNumG];            // ceil(65536 / G): x / G == (x * inv) >> 16 for x < 2048
-};
-// Where every class (packed and wide) starts in the worklist: what scatter_kernel needs.
-struct EntryTab {
-    uint32_t entry_base[kNumClasses];
+    uint32_t entry_base[kNumClasses];     // where the class's records start in the worklist
+    uint32_t count[kNumClasses];          // rows in the class
+    uint32_t order[kNumClasses];          // classes in processing order (largest groups first, long reads before packed rows)
+    uint32_t item_base[kNumClasses + 1];  // batches before the q-th class in processing order
+    uint32_t lanes[kNumClasses];          // G: lanes per row
+    uint32_t rpb[kNumClasses];            // rows per batch
+    uint32_t inv[kNumClasses];            // ceil(65536 / G): x / G == (x * inv) >> 16 for x < 2048
 };
 
 // scratch carve-up
@@ -119,8 +112,7 @@ struct Work {
     uint2 *meta;                     // n_reads: {where the row's bad regions sit in `stage` (pairs), how many}
     uint2 *stage;                    // bad regions in batch-completion order (warps reserve chunks with one atomic)
     uint32_t stage_cap;              // pairs
-    uint32_t *part_total;            // 2 x n_parts: bad regions of every part of kPartRows rows (RED by the sorting kernels); the
-                                     // half of step e & 1 is in use, order_kernel's last CTA zeroes the other one
+    unsigned long long *part_desc;   // n_parts: step tag << 32 | bad regions of the part (order_kernel publishes, later parts sum)
     uint32_t n_parts;
     uint32_t *lit_list;              // rows holding a malformed interval (they take the literal heap sweep)
     uint32_t *bad_rows;              // one bit per row: the row holds a malformed interval (validate_kernel)
@@ -131,7 +123,7 @@ struct Work {
 // ------------------------------------------------------------------------------------------------
 // scatter_kernel: rows -> worklist records grouped by size class (CTA-aggregated cursors)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Work w, EntryTab tab) {
+__global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Work w, ClassTab tab) {
     __shared__ uint32_t s_cnt[kNumClasses], s_base[kNumClasses];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * kScatterRows + tid;
     if (tid < (uint32_t)kNumClasses) s_cnt[tid] = 0u;
@@ -447,7 +439,6 @@ __device__ void cta_row(const DetectArgs &a, const Work &w, uint32_t *cnt, uint3
             atomicAdd(cnt + kCntStageOverflow, 1u);
         }
         w.meta[r] = make_uint2(at, ng);
-        if (ng) atomicAdd(w.part_total + (r >> kPartShift), ng);
     }
     __syncthreads();
 }
@@ -458,7 +449,6 @@ __global__ void __launch_bounds__(kCtaThreads) big_kernel(DetectArgs a, Work w, 
     const uint32_t n_big = min((uint32_t)a.rows.n_big, __ldcg(a.counters + kCntBigList));  // (rows redone by literal_kernel are not listed)
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
-    w.part_total += (ep & 1u) * w.n_parts;  // this step's half
     for (uint32_t j = blockIdx.x; j < n_big; j += gridDim.x) {
         const uint32_t r = w.big_list[j];
         const uint32_t k = a.rowptr[r + 1] - a.rowptr[r];
@@ -529,20 +519,25 @@ __device__ __forceinline__ LaneGeo lane_geo(const ClassTab &tab, uint32_t cls, u
 
 #include "regtier.cuh"
 
-// The item's record for this lane (the record of the row its group sorts) — a plain 16-byte load that
-// nothing touches until the batch is issued, so it stays in flight behind the current batch.
-__device__ __forceinline__ uint4 load_rec(const Work &w, const ClassTab &tab, uint32_t item, uint32_t n_items, uint32_t &q, uint32_t &cls,
-                                          uint32_t lane) {
-    uint4 rec = make_uint4(0, 0, 0, 0);
+// Starts the copy of this lane's record of batch `item` (the record of the row its group sorts) into the warp's
+// shared-memory slot: cp.async, global -> shared without a register in between, so nothing has to stay live (or be
+// spilled, which would wait for the load) across the batch being sorted. Lanes without a row get a zero record.
+__device__ __forceinline__ void fetch_rec(const Work &w, const ClassTab &tab, uint4 *slot, uint32_t item, uint32_t n_items, uint32_t &q,
+                                          uint32_t &cls, uint32_t lane) {
     cls = 0;
-    if (item >= n_items) return rec;
-    while (item >= tab.item_base[q + 1]) ++q;
-    cls = tab.order[q];
-    const LaneGeo geo = lane_geo(tab, cls, lane);
-    const uint32_t e = (item - tab.item_base[q]) * geo.rpb + geo.j;
-    if (geo.in_group && e < tab.count[cls]) rec = __ldg(w.recs + tab.entry_base[cls] + e);
-    return rec;
+    const uint4 *src = nullptr;
+    if (item < n_items) {
+        while (item >= tab.item_base[q + 1]) ++q;
+        cls = tab.order[q];
+        const LaneGeo geo = lane_geo(tab, cls, lane);
+        const uint32_t e = (item - tab.item_base[q]) * geo.rpb + geo.j;
+        if (geo.in_group && e < tab.count[cls]) src = w.recs + tab.entry_base[cls] + e;
+    }
+    if (src) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(slot + lane)), "l"(src) : "memory");
+    else slot[lane] = make_uint4(0, 0, 0, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void fetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // TMA copies of the batch's row slabs into `buf` (one per row, issued by the group's first lane).
 __device__ __forceinline__ void issue_batch(const DetectArgs &a, const ClassTab &tab, uint2 *buf, unsigned long long *bar,
@@ -559,9 +554,14 @@ __device__ __forceinline__ void issue_batch(const DetectArgs &a, const ClassTab 
     if (bytes) tma_load_1d(buf + geo.j * ((uint32_t)kE * geo.G + 2u), a.iv + cs, bytes, bar);
 }
 
-template <bool PK>
-__global__ void __launch_bounds__(kSortThreads, PK ? YB_SORT_MIN_CTAS : 8) sort_kernel(DetectArgs a, Work w, ClassTab tab, uint32_t c, PipeMul pm) {
+// sort_kernel: ONE persistent CTA per SM; its warps run on their own (no barrier after the prologue). Batches are dealt
+// to the CTAs round-robin (CTA b takes batches b, b + gridDim, ...: every SM sees the same mix of classes) and drawn
+// inside a CTA from a shared-memory counter: a global counter would cost every warp an L2 round trip per batch, because
+// ptxas turns any atomic in a divergent region into a warp-aggregated one whose result is broadcast by a shuffle on the
+// spot (no way to keep it in flight behind a batch).
+__global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Work w, ClassTab tab, uint32_t c, PipeMul pm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint32_t s_next;
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
     WarpSmem &ws = *reinterpret_cast<WarpSmem *>(smem_raw + wid * kWarpSmemBytes);
     uint2 *buf = reinterpret_cast<uint2 *>(smem_raw + wid * kWarpSmemBytes + sizeof(WarpSmem));
@@ -569,55 +569,60 @@ __global__ void __launch_bounds__(kSortThreads, PK ? YB_SORT_MIN_CTAS : 8) sort_
         mbar_init(&ws.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    if (threadIdx.x == 0) s_next = 0u;
+    __syncthreads();
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
-    w.part_total += (ep & 1u) * w.n_parts;  // this step's half
-    const uint32_t n_items = tab.item_base[kNumG];
+    const uint32_t n_items = tab.item_base[kNumClasses];
     uint32_t q = 0;
-    // Dynamic schedule (batches cost between 1 and 5 us): a warp draws batch indices from one counter, three batches
-    // ahead, so the atomic's latency hides behind a whole batch. Indices drawn by a warp only grow.
-    auto draw_raw = [&]() {  // lane 0 holds the index; nobody waits for the atomic until the value is broadcast
+    auto draw = [&]() {  // the CTA's next batch (indices drawn by a warp only grow)
         uint32_t t = 0;
-        if (lane == 0) t = atom_add_u32(cnt + (PK ? kCntTile : kCntTileWide), 1u);
-        return t;
+        if (lane == 0) t = atomicAdd(&s_next, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        const uint64_t it = (uint64_t)t * gridDim.x + blockIdx.x;
+        return it < n_items ? (uint32_t)it : n_items;
     };
-    uint32_t item = __shfl_sync(FULL, draw_raw(), 0), item1 = __shfl_sync(FULL, draw_raw(), 0), item2 = __shfl_sync(FULL, draw_raw(), 0);
-    // software pipeline: the record of batch i+2 is loading, the slab copies of batch i+1 are issued as soon as the keys of
-    // batch i are in registers (one slab buffer) and land while batch i is sorted
-    uint32_t cls0, cls1, cls2;
-    uint4 rec0 = load_rec(w, tab, item, n_items, q, cls0, lane);
-    uint4 rec1 = load_rec(w, tab, item1, n_items, q, cls1, lane);
+    uint32_t item = draw(), item1 = draw(), item2 = draw();
+    // software pipeline: the record of batch i+2 is on its way to shared memory, the slab copies of batch i+1 are issued
+    // as soon as the keys of batch i are in registers (one slab buffer) and land while batch i is sorted
+    uint32_t cls0, cls1, cls2, s = 1;  // ws.rec[s]: record of batch i+1; ws.rec[s ^ 1]: of batch i+2
+    fetch_rec(w, tab, ws.rec[0], item, n_items, q, cls0, lane);
+    fetch_rec(w, tab, ws.rec[1], item1, n_items, q, cls1, lane);
+    fetch_wait();
+    uint4 rec0 = ws.rec[0][lane];
     if (item < n_items) issue_batch(a, tab, buf, &ws.mbar, rec0, cls0, lane);
+    fetch_rec(w, tab, ws.rec[0], item2, n_items, q, cls2, lane);
     uint32_t parity = 0;
     uint2 chunk = make_uint2(0, 0);  // [next free pair, end) of the warp's staging chunk
     while (item < n_items) {
-        const uint32_t raw3 = draw_raw();  // consumed at the end of this iteration
-        const uint4 rec2 = load_rec(w, tab, item2, n_items, q, cls2, lane);
         mbar_wait(&ws.mbar, parity);
+        fetch_wait();  // (issued a batch ago)
         auto refill = [&]() {
             // this batch's generic-proxy reads of the slab before the async-proxy writes of the next batch's copies
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (item1 < n_items) issue_batch(a, tab, buf, &ws.mbar, rec1, cls1, lane);
+            if (item1 < n_items) issue_batch(a, tab, buf, &ws.mbar, ws.rec[s][lane], cls1, lane);
         };
-        switch (cls0) {  // G = class_lanes(class)
-            case 0: process_batch_t<1, PK>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
-            case 1: process_batch_t<2, PK>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
-            case 2: process_batch_t<3, PK>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
-            case 3: process_batch_t<4, PK>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
-            case 4: process_batch_t<5, PK>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
-            case 5: process_batch_t<8, PK>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
-            default: process_batch_t<16, PK>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
+#define YB_CASE(gi)                                                                                                        \
+    case gi: process_batch_t<class_lanes_c(gi), true>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;             \
+    case gi + kNumG: process_batch_t<class_lanes_c(gi), false>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
+        switch (cls0) {  // classes 0 .. kNumG-1: packed rows, G = class_lanes(class); kNumG .. : the same sizes for long reads
+            YB_CASE(0) YB_CASE(1) YB_CASE(2) YB_CASE(3) YB_CASE(4) YB_CASE(5) YB_CASE(6)
+#if YB_KE == 16
+            YB_CASE(7) YB_CASE(8) YB_CASE(9)
+#endif
+            default: break;
         }
+#undef YB_CASE
         __syncwarp();
-        rec0 = rec1;
-        rec1 = rec2;
+        rec0 = ws.rec[s][lane];
         cls0 = cls1;
         cls1 = cls2;
         item = item1;
         item1 = item2;
-        item2 = __shfl_sync(FULL, raw3, 0);
+        item2 = draw();
+        fetch_rec(w, tab, ws.rec[s], item2, n_items, q, cls2, lane);
+        s ^= 1u;
         parity ^= 1u;
     }
 }
@@ -626,21 +631,32 @@ constexpr size_t kSortSmemBytes = kWarpSmemBytes * kSortWarps;
 
 // ------------------------------------------------------------------------------------------------
 // ordering pass (order_kernel, the second and last kernel of a detect step): the sorting kernels left, per row, a
-// staging offset and a count, and per part of 2048 rows the part's total (RED). A CTA takes one part, 4 consecutive rows
-// per thread: it sums the totals of the parts before it (at most a few hundred words: no scan kernel, no look-back
-// chain between CTAs), turns counts into offsets (thread-local prefix + block scan), moves the staged regions to their
-// final place, classifies (editor/mod.rs:85-100) and writes the 2-bit bitmap (to every peer's gather buffer when the
-// all-gather is fused in). The last CTA to finish closes the step: it zeroes the other counter set and the other half
-// of the part totals, bumps the step number and, with peers, tells every rank that this rank's slot is complete.
+// staging offset and a count. A CTA takes one part of 2048 rows (in ticket order), 4 consecutive rows per thread: it
+// publishes the part's total in one 64-bit word tagged with the step number (never reset) as soon as its counts are
+// loaded, sums the totals of ALL parts before it (a thousand words at most; it only ever waits for parts that are
+// already running and whose total does not depend on anybody: no scan kernel, no look-back chain, and no RED per row
+// in the sorting kernels, which serialised in L2 when every warp of the GPU worked on the same stretch of rows), turns
+// counts into offsets (thread-local prefix + block scan), moves the staged regions to their final place, classifies
+// (editor/mod.rs:85-100) and writes the 2-bit bitmap (to every peer's gather buffer when the all-gather is fused in).
+// The last CTA to finish closes the step: it zeroes the other counter set, bumps the step number and, with peers, tells
+// every rank that this rank's slot is complete.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kOrderThreads) order_kernel(DetectArgs a, Work w, double not_cov) {
+__device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kOrderThreads, 2) order_kernel(DetectArgs a, Work w, double not_cov) {
     constexpr uint32_t R = kOrderRows, NW = kOrderThreads / 32;
-    __shared__ uint32_t s_warp[NW], s_pre[NW], s_hist[NW], s_last;
+    __shared__ uint32_t s_warp[NW], s_pre[NW], s_hist[NW], s_last, s_part;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
-    const uint32_t *ptot = w.part_total + (ep & 1u) * w.n_parts;
-    const uint32_t part = blockIdx.x, r0 = part * kPartRows + tid * R;
+    if (tid == 0) s_part = atomicAdd(cnt + kCntTicket, 1u);  // parts start in ticket order: a part only waits for parts that run
     uint32_t peer_step = 0;
     if (a.n_peers) {
         // every rank has finished step peer_step - 1 (and, in its stream order, whatever read the gather buffer of step
@@ -657,9 +673,9 @@ __global__ void __launch_bounds__(kOrderThreads) order_kernel(DetectArgs a, Work
             if ((int32_t)(seen - peer_step) < 0) atomicAdd(cnt + kCntPeerTimeout, 1u);
         }
     }
+    __syncthreads();
+    const uint32_t part = s_part, r0 = part * kPartRows + tid * R;
     // everything the rows need is requested up front; the first two regions of a row (most have <= 3) ride along
-    uint32_t pre = 0;
-    for (uint32_t i = tid; i < part; i += kOrderThreads) pre += __ldcg(ptot + i);
     uint2 m[R];
     uint32_t l[R];
     const bool full = r0 + R <= a.n_reads;
@@ -696,8 +712,22 @@ __global__ void __launch_bounds__(kOrderThreads) order_kernel(DetectArgs a, Work
 #pragma unroll
     for (uint32_t i = 0; i < R; ++i) mine += m[i].y;
     const uint32_t incl = warp_incl_scan(mine);
-    pre = __reduce_add_sync(FULL, pre);
     if (lane == 31u) s_warp[wid] = incl;
+    __syncthreads();
+    const unsigned long long tag = (unsigned long long)(ep + 1u) << 32;
+    if (tid == 0) {  // the part's total, for the parts behind this one
+        uint32_t tot = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < NW; ++q) tot += s_warp[q];
+        st_desc(w.part_desc + part, tag | tot);
+    }
+    uint32_t pre = 0;  // totals of the parts before this one (they hold earlier tickets: running or done)
+    for (uint32_t i = tid; i < part; i += kOrderThreads) {
+        unsigned long long d = ld_desc(w.part_desc + i);
+        while ((d >> 32) != (tag >> 32)) d = ld_desc(w.part_desc + i);
+        pre += (uint32_t)d;
+    }
+    pre = __reduce_add_sync(FULL, pre);
     if (lane == 0u) s_pre[wid] = pre;
     __syncthreads();
     uint32_t gp = incl - mine;
@@ -778,11 +808,9 @@ __global__ void __launch_bounds__(kOrderThreads) order_kernel(DetectArgs a, Work
         s_last = atomicAdd(cnt + kCntDone, 1u) == w.n_parts - 1u;
     }
     __syncthreads();
-    if (s_last) {  // the step is complete: next step's counter set and part totals, step number, peers
+    if (s_last) {  // the step is complete: next step's counter set, step number, peers
         uint32_t *other = a.counters + ((ep + 1u) & 1u) * kNumCounters;
         for (uint32_t i = tid; i < kNumCounters; i += kOrderThreads) other[i] = 0u;
-        uint32_t *optot = w.part_total + ((ep + 1u) & 1u) * w.n_parts;
-        for (uint32_t i = tid; i < w.n_parts; i += kOrderThreads) optot[i] = 0u;
         __threadfence();
         __syncthreads();
         if (tid == 0) a.counters[kCntEpoch] = ep + 1u;
@@ -978,7 +1006,6 @@ __device__ __forceinline__ void lit_pop(uint32_t *h, uint32_t &n) {
 __global__ void __launch_bounds__(64) literal_kernel(DetectArgs a, Work w, uint32_t coverage, uint32_t n_lit) {
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
-    w.part_total += (ep & 1u) * w.n_parts;  // this step's half
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_lit; j += gridDim.x * blockDim.x) {
         const uint32_t r = w.lit_list[j];
         const uint32_t s = a.rowptr[r], k = a.rowptr[r + 1] - s, len = a.len[r];
@@ -1036,7 +1063,6 @@ __global__ void __launch_bounds__(64) literal_kernel(DetectArgs a, Work w, uint3
             g[n_clean++] = cur;
         }
         w.meta[r] = make_uint2((uint32_t)(g - w.stage), n_clean);
-        if (n_clean) atomicAdd(w.part_total + (r >> kPartShift), n_clean);
     }
 }
 
@@ -1058,7 +1084,7 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, size_t *tota
     const uint64_t cap = (uint64_t)a.n_iv + a.n_reads + ((uint64_t)a.n_iv + a.n_reads) / 2 + 2ull * a.n_reads + 4096ull * kStageChunk;  // + one open chunk per resident warp
     w.stage_cap = cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cap;
     w.stage = reinterpret_cast<uint2 *>(take(sizeof(uint2) * ((size_t)w.stage_cap + 1)));
-    w.part_total = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (2 * (size_t)w.n_parts + 8)));
+    w.part_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * ((size_t)w.n_parts + 8)));
     w.big_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.huge_keys = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (huge_keys + 1)));
     w.lit_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)a.n_reads + 1)));
@@ -1067,36 +1093,31 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, size_t *tota
     return w;
 }
 
-EntryTab make_entries(const DetectArgs &a) {
-    EntryTab et{};
+// The step's class table: where every class's records sit in the worklist and how its batches are numbered.
+ClassTab make_plan(const DetectArgs &a) {
+    ClassTab tab{};
     uint32_t at = 0;
     for (int cl = 0; cl < kNumClasses; ++cl) {
-        et.entry_base[cl] = at;
-        at += a.rows.class_count[cl];
+        tab.entry_base[cl] = at;
+        tab.count[cl] = a.rows.class_count[cl];
+        at += tab.count[cl];
     }
-    return et;
-}
-
-// The class table of one sorting kernel: where its classes' records sit in the worklist and how its batches are numbered.
-ClassTab make_plan(const DetectArgs &a, bool wide) {
-    const EntryTab et = make_entries(a);
-    ClassTab tab{};
     uint32_t items = 0;
     int q = 0;
-    for (int gi = kNumG - 1; gi >= 0; --gi) {  // batches ordered largest groups first
-        const int cl = gi + (wide ? kNumG : 0);
-        const uint32_t G = class_lanes(gi), rpb = std::min(32u / G, kBufIntervals / ((uint32_t)kE * G + 2u));
-        tab.entry_base[gi] = et.entry_base[cl];
-        tab.count[gi] = a.rows.class_count[cl];
-        tab.lanes[gi] = G;
-        tab.rpb[gi] = rpb;
-        tab.inv[gi] = (65536u + G - 1u) / G;
-        tab.order[q] = (uint32_t)gi;
-        tab.item_base[q] = items;
-        items += (tab.count[gi] + rpb - 1u) / rpb;
-        ++q;
+    for (int wide = 1; wide >= 0; --wide) {  // the few long reads first, then the packed rows; largest groups first
+        for (int gi = kNumG - 1; gi >= 0; --gi) {
+            const int cl = gi + (wide ? kNumG : 0);
+            const uint32_t G = class_lanes(gi), rpb = std::min(32u / G, kBufIntervals / ((uint32_t)kE * G + 2u));
+            tab.lanes[cl] = G;
+            tab.rpb[cl] = rpb;
+            tab.inv[cl] = (65536u + G - 1u) / G;
+            tab.order[q] = (uint32_t)cl;
+            tab.item_base[q] = items;
+            items += (tab.count[cl] + rpb - 1u) / rpb;
+            ++q;
+        }
     }
-    tab.item_base[kNumG] = items;
+    tab.item_base[kNumClasses] = items;
     return tab;
 }
 
@@ -1104,7 +1125,7 @@ ClassTab make_plan(const DetectArgs &a, bool wide) {
 // thread is a supported way to use the library).
 struct DevCfg {
     std::once_flag once;
-    int ok = 0, n_sm = 0, occ_sort = 0, occ_wide = 0;
+    int ok = 0, n_sm = 0, occ_sort = 0;
 };
 DevCfg g_dev[64];
 
@@ -1116,14 +1137,10 @@ const DevCfg *dev_cfg() {
         int sm = 0, occ = 0;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return;
         if (cudaFuncSetAttribute(big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCtaMaxSmemWords * sizeof(uint32_t))) != cudaSuccess) return;
-        int occ_w = 0;
-        if (cudaFuncSetAttribute(sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return;
-        if (cudaFuncSetAttribute(sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_kernel<true>, kSortThreads, kSortSmemBytes) != cudaSuccess || occ < 1) return;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, sort_kernel<false>, kSortThreads, kSortSmemBytes) != cudaSuccess || occ_w < 1) return;
+        if (cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_kernel, kSortThreads, kSortSmemBytes) != cudaSuccess || occ < 1) return;
         d.n_sm = sm;
         d.occ_sort = occ;
-        d.occ_wide = occ_w;
         d.ok = 1;
     });
     if (!d.ok) {
@@ -1154,9 +1171,9 @@ int launch_upload_kernels(const DetectArgs &a, DevRowStats *out, cudaStream_t st
     uint32_t grid = (uint32_t)dc->n_sm * 8u;
     const uint32_t want = (a.n_reads + 255u) / 256u;
     if (grid > want) grid = want;
-    if (cudaMemsetAsync(w.part_total, 0, sizeof(uint32_t) * 2 * (size_t)w.n_parts, stream) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(w.part_desc, 0, sizeof(unsigned long long) * (size_t)w.n_parts, stream) != cudaSuccess) return -1;
     validate_kernel<<<grid, 256, 0, stream>>>(a.iv, a.rowptr, a.len, a.n_reads, out, w.lit_list, a.counters + kCntLiteralList, w.bad_rows);
-    scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, make_entries(a));
+    scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, make_plan(a));
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
@@ -1183,42 +1200,31 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     Work w = carve(a, a.rows.huge_keys, a.rows.n_big, &total);
     if (total > a.scratch_bytes) return -1;
     const PipeMul pm = {1u, 0xFFFFFFFFu, 65536u};
-    // the few rows with more than 512 intervals (CTA tier) and the few reads longer than 65534 bases (the register tier's
-    // u32 variant) run on a side stream, beside the packed register tier: all three only append to the staging buffer
-    const ClassTab wtab = make_plan(a, true);
-    const uint32_t witems = a.rows.n_wide ? wtab.item_base[kNumG] : 0u;
     bool forked = false;
-    if (a.rows.n_big || witems) {
+    if (a.rows.n_big) {
+        // the few rows with more than 512 intervals (CTA tier) run on a side stream, beside the register tier (both only
+        // append to the staging buffer); shared memory for the largest row (wide if any read is); rows beyond
+        // kCtaMaxSmemWords sort in a global slab
         forked = a.side_stream && a.ev_fork && a.ev_join && cudaEventRecord(a.ev_fork, stream) == cudaSuccess &&
                  cudaStreamWaitEvent(a.side_stream, a.ev_fork, 0) == cudaSuccess;
-        const cudaStream_t side = forked ? a.side_stream : stream;
-        if (a.rows.n_big) {
-            // shared memory for the largest row (wide if any read is); rows beyond kCtaMaxSmemWords sort in a global slab
-            uint64_t words = cta_words(a.max_k, a.rows.n_wide != 0);
-            if (words > kCtaMaxSmemWords) words = kCtaMaxSmemWords;
-            uint32_t per_sm = (uint32_t)((220u * 1024u) / (words * 4u + 1024u));
-            if (per_sm < 1u) per_sm = 1u;
-            if (per_sm > 8u) per_sm = 8u;
-            uint32_t grid = (uint32_t)dc->n_sm * per_sm;
-            if (grid > a.rows.n_big) grid = (uint32_t)a.rows.n_big;
-            big_kernel<<<grid, kCtaThreads, words * sizeof(uint32_t), side>>>(a, w, coverage, (uint32_t)words);
-            ++launches;
-        }
-        if (witems) {
-            uint32_t grid = (uint32_t)(dc->n_sm * dc->occ_wide);
-            if (grid > witems) grid = witems;
-            sort_kernel<false><<<grid, kSortThreads, kSortSmemBytes, side>>>(a, w, wtab, coverage, pm);
-            ++launches;
-        }
+        uint64_t words = cta_words(a.max_k, a.rows.n_wide != 0);
+        if (words > kCtaMaxSmemWords) words = kCtaMaxSmemWords;
+        uint32_t per_sm = (uint32_t)((220u * 1024u) / (words * 4u + 1024u));
+        if (per_sm < 1u) per_sm = 1u;
+        if (per_sm > 8u) per_sm = 8u;
+        uint32_t grid = (uint32_t)dc->n_sm * per_sm;
+        if (grid > a.rows.n_big) grid = (uint32_t)a.rows.n_big;
+        big_kernel<<<grid, kCtaThreads, words * sizeof(uint32_t), forked ? a.side_stream : stream>>>(a, w, coverage, (uint32_t)words);
+        ++launches;
         if (forked && cudaEventRecord(a.ev_join, a.side_stream) != cudaSuccess) return -1;
     }
     {
-        const ClassTab tab = make_plan(a, false);
-        const uint32_t items = tab.item_base[kNumG];
+        const ClassTab tab = make_plan(a);
+        const uint32_t items = tab.item_base[kNumClasses];
         if (items) {
-            uint32_t grid = (uint32_t)(dc->n_sm * dc->occ_sort);
+            uint32_t grid = (uint32_t)dc->n_sm;
             if (grid > items) grid = items;
-            sort_kernel<true><<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage, pm);
+            sort_kernel<<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage, pm);
             ++launches;
         }
     }

@@ -41,13 +41,33 @@ constexpr uint32_t kCntClassCursor = 2 * kNumCounters + 8;  // upload: kNumClass
 constexpr uint32_t kCounterWords = 2 * kNumCounters + 8 + 24;
 
 
-// Size classes of the register tier: a row with k intervals is sorted by G lanes x 32 keys, G the smallest
-// entry with 32 G >= k. Classes 0..kNumG-1 hold rows whose positions fit 16 bits (packed u16x2 keys),
+// Size classes of the register tier: a row with k intervals is sorted by G lanes x kE keys, G the smallest entry of
+// kClassLanes with kE G >= k. Classes 0..kNumG-1 hold rows whose positions fit 16 bits (packed u16x2 keys),
 // kNumG..2 kNumG-1 the same sizes for longer reads (two u32 key arrays). Rows with k > 512 are "big".
+#ifndef YB_KE
+#define YB_KE 32   // keys per lane: 32 (a row of up to 64 intervals crosses lanes once) or 16 (half the shared memory per warp)
+#endif
+constexpr int kE = YB_KE;
+#if YB_KE == 32
 constexpr int kNumG = 7;
-constexpr int kNumClasses = 2 * kNumG;
 __host__ __device__ inline uint32_t class_lanes(int gi) {
     return gi == 0 ? 1u : gi == 1 ? 2u : gi == 2 ? 3u : gi == 3 ? 4u : gi == 4 ? 5u : gi == 5 ? 8u : 16u;
+}
+#elif YB_KE == 16
+constexpr int kNumG = 10;
+__host__ __device__ inline uint32_t class_lanes(int gi) {
+    return gi == 0 ? 1u : gi == 1 ? 2u : gi == 2 ? 3u : gi == 3 ? 4u : gi == 4 ? 5u : gi == 5 ? 6u : gi == 6 ? 8u : gi == 7 ? 10u : gi == 8 ? 16u : 32u;
+}
+#else
+#error "YB_KE must be 16 or 32"
+#endif
+constexpr int kNumClasses = 2 * kNumG;
+__host__ __device__ constexpr int class_lanes_c(int gi) {
+#if YB_KE == 32
+    return gi == 0 ? 1 : gi == 1 ? 2 : gi == 2 ? 3 : gi == 3 ? 4 : gi == 4 ? 5 : gi == 5 ? 8 : 16;
+#else
+    return gi == 0 ? 1 : gi == 1 ? 2 : gi == 2 ? 3 : gi == 3 ? 4 : gi == 4 ? 5 : gi == 5 ? 6 : gi == 6 ? 8 : gi == 7 ? 10 : gi == 8 ? 16 : 32;
+#endif
 }
 
 // Rows whose length is <= kPackedMaxLen are sorted as packed u16x2 keys (begin | end << 16).
@@ -57,7 +77,8 @@ constexpr uint32_t kRegisterTierMaxK = 512u;
 // Size class of a row, or -1 for a big row (k > 512).
 __host__ __device__ inline int class_of_row(uint32_t k, uint32_t len) {
     if (k > kRegisterTierMaxK) return -1;
-    const int gi = k <= 32u ? 0 : k <= 64u ? 1 : k <= 96u ? 2 : k <= 128u ? 3 : k <= 160u ? 4 : k <= 256u ? 5 : 6;
+    int gi = 0;
+    while ((uint32_t)kE * class_lanes(gi) < k) ++gi;
     return gi + (len > kPackedMaxLen ? kNumG : 0);
 }
 

@@ -18,12 +18,11 @@
 // the end that is c (+1) ranks below at a warp-uniform offset and push their carries into bit masks (IADD3 + IMAD.X);
 // (4) the handful of crossings U0 D0 U1 D1 ... goes straight to a bump-allocated segment of the staging buffer as the
 // pair list P[q] = (D_{q-1}, U_q) with D_{-1} = 0 and U_{n} = len: the row's bad regions are a sub-range of it, so per row
-// only one 8-byte record {first pair, count} and one RED into the row's part total follow (order_kernel sums those, no
-// scan kernel). The slab is dead as soon as the keys are in registers: the copies of the NEXT batch are issued into the
+// only one 8-byte record {first pair, count} follows (order_kernel does the rest). The slab is dead as soon as the keys are in registers: the copies of the NEXT batch are issued into the
 // same buffer right after the load phase and land while this batch is sorted (one slab + T = 13 KB per warp).
 #pragma once
 
-constexpr int kE = 32;                       // keys per lane per array
+constexpr int kLogE = kE == 32 ? 5 : 4;
 constexpr uint32_t kScrPitch2 = 33;          // T[t][lane] at scr[1 + 33 t + lane]; scr[0] stands for lane -1
 constexpr uint32_t kScrWords2 = (uint32_t)kE * kScrPitch2 + 4u;
 
@@ -40,7 +39,10 @@ template <int G> struct Geo {
     static constexpr int PITCH = kE * G + 2;  // row slots of the slab buffer (host: make_plan)
     static constexpr int RPB = (32 / G) < ((int)kBufIntervals / PITCH) ? (32 / G) : ((int)kBufIntervals / PITCH);
     // rows of the class have more than KMIN intervals (class_of_row picks the smallest class that fits); -1: any k >= 0
-    static constexpr int KMIN = G == 1 ? -1 : G == 2 ? 32 : G == 3 ? 64 : G == 4 ? 96 : G == 5 ? 128 : G == 8 ? 160 : 256;
+    static __host__ __device__ constexpr int prev_lanes(int gi = 0, int p = 0) {
+        return gi >= kNumG ? p : class_lanes_c(gi) == G ? p : prev_lanes(gi + 1, class_lanes_c(gi));
+    }
+    static constexpr int KMIN = G == 1 ? -1 : kE * prev_lanes();
     static_assert(kPow2 || RPB * G <= 31, "a group that is not a power of two needs spare lane 31");
 };
 
@@ -82,8 +84,9 @@ template <bool PK, int O> __device__ __forceinline__ void sort16_t(uint32_t (&k)
 // the lane's 32 keys: two sorted halves, then Batcher's odd-even merge of 16 + 16 (65 exchanges)
 template <bool PK> __device__ __forceinline__ void sort32_t(uint32_t (&k)[kE], const PipeMul pm) {
     sort16_t<PK, 0>(k, pm);
-    sort16_t<PK, 16>(k, pm);
-#define CE(n, i, j) ce_t<PK>(k[i], k[j], pm, n + 1);
+    if (kE < 32) return;
+    sort16_t<PK, kE - 16>(k, pm);
+#define CE(n, i, j) ce_t<PK>(k[(i) % kE], k[(j) % kE], pm, n + 1);
     CE(0, 0, 16) CE(1, 8, 24) CE(2, 8, 16) CE(3, 4, 20) CE(4, 12, 28) CE(5, 12, 20) CE(6, 4, 8) CE(7, 12, 16)
     CE(8, 20, 24) CE(9, 2, 18) CE(10, 10, 26) CE(11, 10, 18) CE(12, 6, 22) CE(13, 14, 30) CE(14, 14, 22) CE(15, 6, 10)
     CE(16, 14, 18) CE(17, 22, 26) CE(18, 2, 4) CE(19, 6, 8) CE(20, 10, 12) CE(21, 14, 16) CE(22, 18, 20) CE(23, 22, 24)
@@ -106,6 +109,25 @@ template <bool PK> __device__ __forceinline__ void clean32_t(uint32_t (&k)[kE], 
     }
 }
 
+// k_i = keep_min ? min(k_i, o_i) : max(k_i, o_i) for four keys, in place: one SETP, four predicated pairs
+template <bool PK>
+__device__ __forceinline__ void xsel4(uint32_t &k0, uint32_t &k1, uint32_t &k2, uint32_t &k3, uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3,
+                                      uint32_t keep_min) {
+    if (PK) {
+        asm("{\n.reg .pred p;\nsetp.ne.u32 p, %8, 0;\n"
+            "@p min.u16x2 %0, %0, %4;\n@!p max.u16x2 %0, %0, %4;\n@p min.u16x2 %1, %1, %5;\n@!p max.u16x2 %1, %1, %5;\n"
+            "@p min.u16x2 %2, %2, %6;\n@!p max.u16x2 %2, %2, %6;\n@p min.u16x2 %3, %3, %7;\n@!p max.u16x2 %3, %3, %7;\n}"
+            : "+r"(k0), "+r"(k1), "+r"(k2), "+r"(k3)
+            : "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(keep_min));
+    } else {
+        asm("{\n.reg .pred p;\nsetp.ne.u32 p, %8, 0;\n"
+            "@p min.u32 %0, %0, %4;\n@!p max.u32 %0, %0, %4;\n@p min.u32 %1, %1, %5;\n@!p max.u32 %1, %1, %5;\n"
+            "@p min.u32 %2, %2, %6;\n@!p max.u32 %2, %2, %6;\n@p min.u32 %3, %3, %7;\n@!p max.u32 %3, %3, %7;\n}"
+            : "+r"(k0), "+r"(k1), "+r"(k2), "+r"(k3)
+            : "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(keep_min));
+    }
+}
+
 // One exchange stage between lanes: lane g with lane g ^ M of its group (FLIP: my slot t against its slot 31 - t).
 // The min / max choice is a per-lane predicate; ptxas turns it into a predicated pair of VIMNMX (it never emits the
 // single instruction with a predicate operand), which is why 32 keys per lane pay: a row of up to 64 intervals
@@ -124,25 +146,30 @@ __device__ __forceinline__ void xlane_t(uint32_t (&key)[kE], const uint32_t lane
         src = ex ? lane + partner - g : 31u;
         keep_min = !ex || (g & HB) == 0u;
     }
-    auto pick = [&](uint32_t mine, uint32_t theirs) {
-        return keep_min ? (PK ? __vminu2(mine, theirs) : min(mine, theirs)) : (PK ? __vmaxu2(mine, theirs) : max(mine, theirs));
-    };
+    // (inline PTX, four keys per block: from C++ - select or if / else alike - ptxas builds min and max into two fresh
+    // registers and adds two predicated moves per key)
+    const uint32_t km = keep_min ? 1u : 0u;
     if (FLIP) {
 #pragma unroll
-        for (int t = 0; t < kE / 2; ++t) {
-            const uint32_t o_hi = __shfl_sync(FULL, key[kE - 1 - t], src), o_lo = __shfl_sync(FULL, key[t], src);
-            key[t] = pick(key[t], o_hi);
-            key[kE - 1 - t] = pick(key[kE - 1 - t], o_lo);
+        for (int t = 0; t < kE / 2; t += 2) {
+            const uint32_t a0 = __shfl_sync(FULL, key[kE - 1 - t], src), b0 = __shfl_sync(FULL, key[t], src);
+            const uint32_t a1 = __shfl_sync(FULL, key[kE - 2 - t], src), b1 = __shfl_sync(FULL, key[t + 1], src);
+            xsel4<PK>(key[t], key[kE - 1 - t], key[t + 1], key[kE - 2 - t], a0, b0, a1, b1, km);
         }
     } else {
 #pragma unroll
-        for (int t = 0; t < kE; ++t) key[t] = pick(key[t], __shfl_sync(FULL, key[t], src));
+        for (int t = 0; t < kE; t += 4) {
+            const uint32_t o0 = __shfl_sync(FULL, key[t], src), o1 = __shfl_sync(FULL, key[t + 1], src);
+            const uint32_t o2 = __shfl_sync(FULL, key[t + 2], src), o3 = __shfl_sync(FULL, key[t + 3], src);
+            xsel4<PK>(key[t], key[t + 1], key[t + 2], key[t + 3], o0, o1, o2, o3, km);
+        }
     }
 }
 
 template <int G, int LS, bool PK>
 __device__ __forceinline__ void merge_level_t(uint32_t (&key)[kE], const uint32_t lane, const uint32_t g, const bool in_group, const PipeMul pm) {
     xlane_t<G, LS - 1, true, PK>(key, lane, g, in_group);
+    if (LS >= 32) xlane_t<G, 8, false, PK>(key, lane, g, in_group);
     if (LS >= 16) xlane_t<G, 4, false, PK>(key, lane, g, in_group);
     if (LS >= 8) xlane_t<G, 2, false, PK>(key, lane, g, in_group);
     if (LS >= 4) xlane_t<G, 1, false, PK>(key, lane, g, in_group);
@@ -158,11 +185,13 @@ __device__ __forceinline__ void sort_group_t(uint32_t (&key)[kE], const uint32_t
     if (NP >= 4) merge_level_t<G, 4, PK>(key, lane, g, in_group, pm);
     if (NP >= 8) merge_level_t<G, 8, PK>(key, lane, g, in_group, pm);
     if (NP >= 16) merge_level_t<G, 16, PK>(key, lane, g, in_group, pm);
+    if (NP >= 32) merge_level_t<G, 32, PK>(key, lane, g, in_group, pm);
 }
 
 struct alignas(16) WarpSmem {  // one per warp: a warp runs on its own, no CTA-wide barrier anywhere
     unsigned long long mbar;
     unsigned long long pad_;
+    uint4 rec[2][32];  // worklist records of the next two batches, one per lane (cp.async)
     uint32_t scr[kScrWords2];
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "the slab must stay 16-byte aligned");
@@ -195,49 +224,44 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
     uint2 *slot = buf + (in_group ? j : 0u) * (uint32_t)GG::PITCH + (rec.y & 1u);  // the row's data starts here
     // striped load (conflict-free); the initial arrangement is irrelevant to the sort. Element t * G + g exists iff
     // t * G < k - g; the test is only compiled for slots a row of this class can end in.
-    uint32_t K0[kE];            // PK: begin | end << 16; else begins
-    uint32_t K1[PK ? 1 : kE];   // else ends
-    {
-        const uint2 *lane_iv = slot + g;
-        const uint32_t left = k > g ? k - g : 0u;
+    // PK: begin | end << 16. Long reads (!PK) sort their ends first (-> T) and then their begins in the SAME registers:
+    // the slab is read twice and refilled after the second load.
+    uint32_t K0[kE];
+    const uint2 *lane_iv = slot + g;
+    const uint32_t left = k > g ? k - g : 0u;
+    auto load_keys = [&](const bool ends) {
 #pragma unroll
         for (int t = 0; t < kE; ++t) {
             const uint2 v = lane_iv[t * G];
             // (spare lanes - 31 above all - hold +inf for xlane_t when the group is not a power of two)
             const bool absent = (t * G + G - 1 > GG::KMIN && !((uint32_t)(t * G) < left)) || (!GG::kPow2 && !in_group);
-            if (PK) {
-                uint32_t key;
-                if (YB_PACK_IMAD) asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(v.y), "r"(pm.shl16), "r"(v.x));
-                else key = __byte_perm(v.x, v.y, 0x5410);
-                K0[t] = absent ? INF : key;
-            } else {
-                K0[t] = absent ? INF : v.x;
-                K1[PK ? 0 : t] = absent ? INF : v.y;
-            }
+            uint32_t key;
+            if (!PK) key = ends ? v.y : v.x;
+            else if (YB_PACK_IMAD) asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(v.y), "r"(pm.shl16), "r"(v.x));
+            else key = __byte_perm(v.x, v.y, 0x5410);
+            K0[t] = absent ? INF : key;
         }
-    }
-    refill();
-    if (PK) {
-        sort_group_t<G, true>(K0, lane, g, in_group, pm);
-    } else {
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {  // rolled: one copy of the network sorts begins, then ends
-            sort_group_t<G, false>(K0, lane, g, in_group, pm);
-#pragma unroll
-            for (int t = 0; t < kE; ++t) {
-                const uint32_t x = K0[t];
-                K0[t] = K1[PK ? 0 : t];
-                K1[PK ? 0 : t] = x;
-            }
-        }
-    }
+    };
     // transposed copy of the sorted ends (PK: of the packed keys; the compares only look at the end half): T[t][lane];
-    // element 32 l + t - c - 1 is then T[(t - c - 1) & 31][l + ((t - c - 1) >> 5)], a warp-uniform offset from the lane's
-    // own column: conflict-free writes and reads, no per-element index arithmetic
+    // element kE l + t - c - 1 is then T[(t - c - 1) % kE][l + floor((t - c - 1) / kE)], a warp-uniform offset from the
+    // lane's own column: conflict-free writes and reads, no per-element index arithmetic
     uint32_t *T = ws.scr + 1u + lane;
+    if (PK) {
+        load_keys(false);
+        refill();
+        sort_group_t<G, PK>(K0, lane, g, in_group, pm);
+    } else {
+        load_keys(true);
+        sort_group_t<G, PK>(K0, lane, g, in_group, pm);
+    }
     __syncwarp();
 #pragma unroll
-    for (int t = 0; t < kE; ++t) T[kScrPitch2 * t] = PK ? K0[t] : K1[PK ? 0 : t];
+    for (int t = 0; t < kE; ++t) T[kScrPitch2 * t] = K0[t];
+    if (!PK) {
+        load_keys(false);
+        refill();
+        sort_group_t<G, PK>(K0, lane, g, in_group, pm);
+    }
     __syncwarp();
     // V1_t = (E[32g + t - c - 1] <= B_t), t = 0..32;  V0_t = (E[32g + t - c] <= B_t), t = 0..31.
     // PK: (end_j <= begin_i)  <=>  key_j <= (begin_i << 16 | 0xFFFF) as plain u32.
@@ -251,7 +275,7 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
 #pragma unroll
         for (int t = 0; t <= kE; ++t) {
             const int jr = t - (int)cc - 1;  // uniform
-            int col = jr >> 5;
+            int col = jr >> kLogE;
             if (cc >= (uint32_t)kE) col = max(col, -(int)lane - 1);  // stay inside scr; those elements are forced below
             const uint32_t ev = T[(int)kScrPitch2 * (jr & (kE - 1)) + col];
             const uint32_t kt = t < kE ? K0[t % kE] : Knext;
@@ -265,6 +289,8 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
             qp = q;
         }
         // elements below the row's first end are 0 (E[-1] = 0): V1_t true for 32g + t <= c, V0_t for 32g + t < c
+        m1 <<= 32 - kE;
+        m0 <<= 32 - kE;
         const int z = (int)cc - kE * (int)g;
         if (z >= 0) {
             m1 |= top_bits((uint32_t)z + 1u);
@@ -272,8 +298,9 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
             if (z >= kE) v1n = 1u;
         }
     }
-    // bit (31 - t): U at begin t = V1_t & !V0_t; D at end t = !V0_t & V1_{t+1}
-    uint32_t um = m1 & ~m0, dm = ((m1 << 1) | v1n) & ~m0;
+    // kE bits were pushed: move them to the top of the word, then bit (31 - t): U at begin t = V1_t & !V0_t; D at end t =
+    // !V0_t & V1_{t+1}
+    uint32_t um = (m1 & ~m0) & top_bits(kE), dm = (((m1 << 1) | (v1n << (32 - kE))) & ~m0) & top_bits(kE);
     if (!valid) um = dm = 0;
     // ranks of this lane's crossings among the row's ups / downs (packed segmented scan over the group)
     const uint32_t mine = __popc(um) | (__popc(dm) << 16);
@@ -299,7 +326,7 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
         }
         if (dm) {
             const int jr = 32 - __ffs(dm) - (int)cc;  // slot t = 31 - (ffs - 1)
-            ld = T[(int)kScrPitch2 * (jr & (kE - 1)) + (jr >> 5)];
+            ld = T[(int)kScrPitch2 * (jr & (kE - 1)) + (jr >> kLogE)];
             if (PK) ld >>= 16;
         }
         if (G == 1) {
@@ -356,7 +383,7 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
             const int t = __clz(dm);
             dm &= ~(0x80000000u >> t);
             const int jr = t - (int)cc;
-            P[2u * rd++ + 2u] = T[(int)kScrPitch2 * (jr & (kE - 1)) + (jr >> 5)] >> 16;
+            P[2u * rd++ + 2u] = T[(int)kScrPitch2 * (jr & (kE - 1)) + (jr >> kLogE)] >> 16;
         }
     } else if (um | dm) {
 #pragma unroll
@@ -364,7 +391,7 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
             if (um & (0x80000000u >> t)) P[2u * ru++ + 1u] = K0[t];
             if (dm & (0x80000000u >> t)) {
                 const int jr = t - (int)cc;
-                P[2u * rd++ + 2u] = T[(int)kScrPitch2 * (jr & (kE - 1)) + (jr >> 5)];
+                P[2u * rd++ + 2u] = T[(int)kScrPitch2 * (jr & (kE - 1)) + (jr >> kLogE)];
             }
         }
     }
@@ -374,6 +401,5 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
         const uint32_t q0 = n_up ? (U0 == 0u) : 0u;
         const uint32_t ng = n_up ? n_up + (Dl != len) - q0 : (len != 0u);
         w.meta[rec.x] = make_uint2(base + q0, ng);
-        if (ng) red_add_u32(w.part_total + (rec.x >> kPartShift), ng);
     }
 }
