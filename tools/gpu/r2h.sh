@@ -31,6 +31,6 @@ for v in $VARIANTS; do
   run $v
 done
 unset YB_LIB_PATH
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:order_kernel -s 3 -c 1 -o $O/${T}_order python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-configs --e2e-steps 1 > $O/${T}_ncu_order.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sort_kernel -s 3 -c 1 -o $O/${T}_sort python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-configs --e2e-steps 1 > $O/${T}_ncu_order.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:validate_kernel -s 0 -c 1 -o $O/${T}_validate python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-configs --e2e-steps 1 > $O/${T}_ncu_validate.log 2>&1
-tail -2 $O/${T}_ncu_order.log
+tail -2 $O/${T}_ncu_order.log 2>/dev/null

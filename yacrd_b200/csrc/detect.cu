@@ -90,8 +90,10 @@ constexpr uint32_t kSortThreads = kSortWarps * 32;
 constexpr uint32_t kBufIntervals = YB_BUF_INTERVALS;  // row slots of a warp's slab buffer: a batch of class G holds min(floor(32 / G),
                                                       // floor(kBufIntervals / (kE G + 2))) rows; 32 (kE + 2) = 32 rows of the G = 1 class
 constexpr uint32_t kScatterRows = 1024;        // rows per CTA of scatter_kernel
-constexpr uint32_t kPartShift = 11, kPartRows = 1u << kPartShift;  // rows per CTA of order_kernel (kOrderThreads x kOrderRows)
-constexpr uint32_t kOrderThreads = 512, kOrderRows = kPartRows / kOrderThreads;
+#ifndef YB_ORDER_THREADS
+#define YB_ORDER_THREADS 256
+#endif
+constexpr uint32_t kOrderThreads = YB_ORDER_THREADS, kOrderRows = 4, kPartRows = kOrderThreads * kOrderRows;  // rows per CTA of order_kernel
 constexpr uint32_t kStageChunk = 2048;       // pairs a warp reserves in the staging buffer per atomic (an L2 round trip the warp waits for)
 constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
 
@@ -575,14 +577,25 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
     const uint32_t n_items = tab.item_base[kNumClasses];
     uint32_t q = 0;
-    auto draw = [&]() {  // the CTA's next batch (indices drawn by a warp only grow)
+#ifdef YB_STATIC_SCHED
+    uint32_t local_next = wid;
+    auto draw_raw = [&]() {  // fixed deal inside the CTA as well: warp w takes the CTA's batches w, w + WARPS, ...
+        const uint32_t t = local_next;
+        local_next += kSortWarps;
+        return t;
+    };
+#else
+    auto draw_raw = [&]() {  // the CTA's next batch (lane 0 holds it; indices drawn by a warp only grow)
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(&s_next, 1u);
-        t = __shfl_sync(FULL, t, 0);
-        const uint64_t it = (uint64_t)t * gridDim.x + blockIdx.x;
+        return t;
+    };
+#endif
+    auto draw_done = [&](uint32_t raw) {  // (called a batch after draw_raw: the shared-memory atomic has long returned)
+        const uint64_t it = (uint64_t)__shfl_sync(FULL, raw, 0) * gridDim.x + blockIdx.x;
         return it < n_items ? (uint32_t)it : n_items;
     };
-    uint32_t item = draw(), item1 = draw(), item2 = draw();
+    uint32_t item = draw_done(draw_raw()), item1 = draw_done(draw_raw()), item2 = draw_done(draw_raw());
     // software pipeline: the record of batch i+2 is on its way to shared memory, the slab copies of batch i+1 are issued
     // as soon as the keys of batch i are in registers (one slab buffer) and land while batch i is sorted
     uint32_t cls0, cls1, cls2, s = 1;  // ws.rec[s]: record of batch i+1; ws.rec[s ^ 1]: of batch i+2
@@ -595,6 +608,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
     uint32_t parity = 0;
     uint2 chunk = make_uint2(0, 0);  // [next free pair, end) of the warp's staging chunk
     while (item < n_items) {
+        const uint32_t raw3 = draw_raw();  // consumed at the end of this iteration
         mbar_wait(&ws.mbar, parity);
         fetch_wait();  // (issued a batch ago)
         auto refill = [&]() {
@@ -620,7 +634,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
         cls1 = cls2;
         item = item1;
         item1 = item2;
-        item2 = draw();
+        item2 = draw_done(raw3);
         fetch_rec(w, tab, ws.rec[s], item2, n_items, q, cls2, lane);
         s ^= 1u;
         parity ^= 1u;
@@ -650,7 +664,7 @@ __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long lon
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kOrderThreads, 2) order_kernel(DetectArgs a, Work w, double not_cov) {
+__global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_kernel(DetectArgs a, Work w, double not_cov) {
     constexpr uint32_t R = kOrderRows, NW = kOrderThreads / 32;
     __shared__ uint32_t s_warp[NW], s_pre[NW], s_hist[NW], s_last, s_part;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
@@ -920,30 +934,42 @@ __global__ void __launch_bounds__(256) validate_kernel(const uint2 *__restrict__
     const uint32_t lane = lane_id(), warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     uint32_t bad = 0, bad_rows = 0;
     for (uint32_t r0 = warp * 32u; r0 < n_reads; r0 += n_warps * 32u) {
-        const uint32_t r = r0 + lane;
-        uint32_t p0 = 0, p1 = 0, l = 0;
-        if (r < n_reads) {
-            p0 = __ldg(rowptr + r);
-            p1 = __ldg(rowptr + r + 1);
-            l = __ldg(len + r);
-        }
-        const uint32_t rows = min(32u, n_reads - r0);
-        uint32_t word = 0;  // bit j: row r0 + j holds a malformed interval
-        for (uint32_t j = 0; j < rows; ++j) {
-            const uint32_t b = __shfl_sync(FULL, p0, j), e = __shfl_sync(FULL, p1, j), lj = __shfl_sync(FULL, l, j);
-            uint32_t row_bad = 0;
-            for (uint32_t i = b + lane; i < e; i += 32u) {
-                const uint2 v = __ldg(iv + i);
-                row_bad += !(v.x < v.y && v.y <= lj);
+        // the 32 rows are one contiguous stretch [P0, P1) of the interval buffer: the warp streams it 32 intervals at a
+        // time (coalesced, the next step's load already in flight) and finds each interval's row from the row ends the
+        // lanes hold (a row ends inside a step of 32 about every other step)
+        const uint32_t r = min(r0 + lane, n_reads - 1u);
+        const uint32_t p1 = __ldg(rowptr + r + 1), l = __ldg(len + r);
+        const uint32_t P0 = __ldg(rowptr + r0), P1 = __shfl_sync(FULL, p1, 31);
+        uint32_t word = 0, cur = 0;  // bit j: row r0 + j holds a malformed interval; cur: first row that ends behind the last step
+        uint2 v = make_uint2(0u, 1u);
+        if (P0 + lane < P1) v = __ldg(iv + P0 + lane);
+        for (uint32_t base = P0; base < P1; base += 32u) {
+            const uint32_t i = base + lane;
+            const uint2 vc = v;
+            if (i + 32u < P1) v = __ldg(iv + i + 32u);
+            uint32_t row = cur, rr = cur;
+            for (; rr < 32u; ++rr) {  // rows that end inside this step (uniform loop)
+                const uint32_t e = __shfl_sync(FULL, p1, rr);
+                if (e > base + 31u) break;
+                row += e <= i;
             }
-            bad += row_bad;
-            if (__any_sync(FULL, row_bad != 0u)) {  // rare
-                if (lane == 0) lit_list[atomicAdd(lit_count, 1u)] = r0 + j;
-                ++bad_rows;
-                word |= 1u << j;
+            cur = rr;
+            const uint32_t lj = __shfl_sync(FULL, l, min(row, 31u));
+            if (i < P1 && !(vc.x < vc.y && vc.y <= lj)) {
+                ++bad;
+                word |= 1u << row;
             }
         }
+        word = __reduce_or_sync(FULL, word);
         if (lane == 0) bad_row_bits[r0 >> 5] = word;
+        if (word) {  // rare
+            bad_rows += __popc(word);
+            if (lane == 0) {
+                const uint32_t at = atomicAdd(lit_count, (uint32_t)__popc(word));
+                uint32_t q = 0;
+                for (uint32_t m = word; m; m &= m - 1u) lit_list[at + q++] = r0 + (uint32_t)__ffs(m) - 1u;
+            }
+        }
     }
     bad = warp_sum(bad);
     if (lane == 0 && bad) {
@@ -1102,20 +1128,22 @@ ClassTab make_plan(const DetectArgs &a) {
         tab.count[cl] = a.rows.class_count[cl];
         at += tab.count[cl];
     }
+    // processing order: largest groups first (the cheap batches last make a fine-grained tail); the few long reads (their
+    // code is cold and they refill late) go behind the first packed class, in the middle of everybody's work
+    int seq[kNumClasses], n_seq = 0;
+    seq[n_seq++] = kNumG - 1;
+    for (int gi = kNumG - 1; gi >= 0; --gi) seq[n_seq++] = gi + kNumG;
+    for (int gi = kNumG - 2; gi >= 0; --gi) seq[n_seq++] = gi;
     uint32_t items = 0;
-    int q = 0;
-    for (int wide = 1; wide >= 0; --wide) {  // the few long reads first, then the packed rows; largest groups first
-        for (int gi = kNumG - 1; gi >= 0; --gi) {
-            const int cl = gi + (wide ? kNumG : 0);
-            const uint32_t G = class_lanes(gi), rpb = std::min(32u / G, kBufIntervals / ((uint32_t)kE * G + 2u));
-            tab.lanes[cl] = G;
-            tab.rpb[cl] = rpb;
-            tab.inv[cl] = (65536u + G - 1u) / G;
-            tab.order[q] = (uint32_t)cl;
-            tab.item_base[q] = items;
-            items += (tab.count[cl] + rpb - 1u) / rpb;
-            ++q;
-        }
+    for (int q = 0; q < kNumClasses; ++q) {
+        const int cl = seq[q], gi = cl % kNumG;
+        const uint32_t G = class_lanes(gi), rpb = std::min(32u / G, kBufIntervals / ((uint32_t)kE * G + 2u));
+        tab.lanes[cl] = G;
+        tab.rpb[cl] = rpb;
+        tab.inv[cl] = (65536u + G - 1u) / G;
+        tab.order[q] = (uint32_t)cl;
+        tab.item_base[q] = items;
+        items += (tab.count[cl] + rpb - 1u) / rpb;
     }
     tab.item_base[kNumClasses] = items;
     return tab;

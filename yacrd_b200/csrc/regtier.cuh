@@ -109,83 +109,63 @@ template <bool PK> __device__ __forceinline__ void clean32_t(uint32_t (&k)[kE], 
     }
 }
 
-// k_i = keep_min ? min(k_i, o_i) : max(k_i, o_i) for four keys, in place: one SETP, four predicated pairs
-template <bool PK>
-__device__ __forceinline__ void xsel4(uint32_t &k0, uint32_t &k1, uint32_t &k2, uint32_t &k3, uint32_t o0, uint32_t o1, uint32_t o2, uint32_t o3,
-                                      uint32_t keep_min) {
-    if (PK) {
-        asm("{\n.reg .pred p;\nsetp.ne.u32 p, %8, 0;\n"
-            "@p min.u16x2 %0, %0, %4;\n@!p max.u16x2 %0, %0, %4;\n@p min.u16x2 %1, %1, %5;\n@!p max.u16x2 %1, %1, %5;\n"
-            "@p min.u16x2 %2, %2, %6;\n@!p max.u16x2 %2, %2, %6;\n@p min.u16x2 %3, %3, %7;\n@!p max.u16x2 %3, %3, %7;\n}"
-            : "+r"(k0), "+r"(k1), "+r"(k2), "+r"(k3)
-            : "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(keep_min));
-    } else {
-        asm("{\n.reg .pred p;\nsetp.ne.u32 p, %8, 0;\n"
-            "@p min.u32 %0, %0, %4;\n@!p max.u32 %0, %0, %4;\n@p min.u32 %1, %1, %5;\n@!p max.u32 %1, %1, %5;\n"
-            "@p min.u32 %2, %2, %6;\n@!p max.u32 %2, %2, %6;\n@p min.u32 %3, %3, %7;\n@!p max.u32 %3, %3, %7;\n}"
-            : "+r"(k0), "+r"(k1), "+r"(k2), "+r"(k3)
-            : "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(keep_min));
-    }
-}
-
-// One exchange stage between lanes: lane g with lane g ^ M of its group (FLIP: my slot t against its slot 31 - t).
-// The min / max choice is a per-lane predicate; ptxas turns it into a predicated pair of VIMNMX (it never emits the
-// single instruction with a predicate operand), which is why 32 keys per lane pay: a row of up to 64 intervals
-// crosses lanes once.
-template <int G, int M, bool FLIP, bool PK>
-__device__ __forceinline__ void xlane_t(uint32_t (&key)[kE], const uint32_t lane, const uint32_t g, const bool in_group) {
-    constexpr uint32_t HB = FLIP ? (uint32_t)(M + 1) >> 1 : (uint32_t)M;  // the bit that tells the lower lane of a pair from the upper
+// One exchange stage between lanes: lane g with lane g ^ M of its group (FLIP: my slot t against its slot kE - 1 - t);
+// M is a run-time value so that every level of the merge runs through the same code (the bodies of the larger classes
+// would not fit the instruction cache otherwise). The min / max choice is a per-lane predicate; ptxas turns it into two
+// VIMNMX into fresh registers plus two predicated moves per key whatever the source looks like (select, if / else,
+// predicated inline PTX) and never emits the single instruction with a predicate operand, which is why 32 keys per lane
+// pay: a row of up to 64 intervals crosses lanes once.
+template <int G, bool FLIP, bool PK>
+__device__ __forceinline__ void xlane_t(uint32_t (&key)[kE], const uint32_t M, const uint32_t lane, const uint32_t g, const bool in_group) {
+    const uint32_t HB = FLIP ? (M + 1u) >> 1 : M;  // the bit that tells the lower lane of a pair from the upper
     uint32_t src;
     bool keep_min;
     if (Geo<G>::kPow2) {
-        src = lane ^ (uint32_t)M;
+        src = lane ^ M;
         keep_min = (lane & HB) == 0u;
     } else {  // the network of NP lanes whose lanes G .. NP-1 hold +inf: spare lane 31 stands for them
-        const uint32_t partner = g ^ (uint32_t)M;
+        const uint32_t partner = g ^ M;
         const bool ex = in_group && partner < (uint32_t)G;
         src = ex ? lane + partner - g : 31u;
         keep_min = !ex || (g & HB) == 0u;
     }
-    // (inline PTX, four keys per block: from C++ - select or if / else alike - ptxas builds min and max into two fresh
-    // registers and adds two predicated moves per key)
-    const uint32_t km = keep_min ? 1u : 0u;
     if (FLIP) {
 #pragma unroll
-        for (int t = 0; t < kE / 2; t += 2) {
-            const uint32_t a0 = __shfl_sync(FULL, key[kE - 1 - t], src), b0 = __shfl_sync(FULL, key[t], src);
-            const uint32_t a1 = __shfl_sync(FULL, key[kE - 2 - t], src), b1 = __shfl_sync(FULL, key[t + 1], src);
-            xsel4<PK>(key[t], key[kE - 1 - t], key[t + 1], key[kE - 2 - t], a0, b0, a1, b1, km);
+        for (int t = 0; t < kE / 2; ++t) {
+            const uint32_t o_hi = __shfl_sync(FULL, key[kE - 1 - t], src), o_lo = __shfl_sync(FULL, key[t], src);
+            if (keep_min) {
+                key[t] = PK ? __vminu2(key[t], o_hi) : min(key[t], o_hi);
+                key[kE - 1 - t] = PK ? __vminu2(key[kE - 1 - t], o_lo) : min(key[kE - 1 - t], o_lo);
+            } else {
+                key[t] = PK ? __vmaxu2(key[t], o_hi) : max(key[t], o_hi);
+                key[kE - 1 - t] = PK ? __vmaxu2(key[kE - 1 - t], o_lo) : max(key[kE - 1 - t], o_lo);
+            }
         }
     } else {
 #pragma unroll
-        for (int t = 0; t < kE; t += 4) {
-            const uint32_t o0 = __shfl_sync(FULL, key[t], src), o1 = __shfl_sync(FULL, key[t + 1], src);
-            const uint32_t o2 = __shfl_sync(FULL, key[t + 2], src), o3 = __shfl_sync(FULL, key[t + 3], src);
-            xsel4<PK>(key[t], key[t + 1], key[t + 2], key[t + 3], o0, o1, o2, o3, km);
+        for (int t = 0; t < kE; ++t) {
+            const uint32_t o = __shfl_sync(FULL, key[t], src);
+            if (keep_min) key[t] = PK ? __vminu2(key[t], o) : min(key[t], o);
+            else key[t] = PK ? __vmaxu2(key[t], o) : max(key[t], o);
         }
     }
 }
 
-template <int G, int LS, bool PK>
-__device__ __forceinline__ void merge_level_t(uint32_t (&key)[kE], const uint32_t lane, const uint32_t g, const bool in_group, const PipeMul pm) {
-    xlane_t<G, LS - 1, true, PK>(key, lane, g, in_group);
-    if (LS >= 32) xlane_t<G, 8, false, PK>(key, lane, g, in_group);
-    if (LS >= 16) xlane_t<G, 4, false, PK>(key, lane, g, in_group);
-    if (LS >= 8) xlane_t<G, 2, false, PK>(key, lane, g, in_group);
-    if (LS >= 4) xlane_t<G, 1, false, PK>(key, lane, g, in_group);
-    clean32_t<PK>(key, pm);
-}
-
-// Sorts, for every group of G consecutive lanes, its 32 G keys (ascending in element order g * 32 + t).
+// Sorts, for every group of G consecutive lanes, its kE G keys (ascending in element order g * kE + t): the lane's own keys,
+// then ceil(log2 G) bitonic merge levels (rolled: one copy of the flip stage, of the lane-bit stage and of the slot-bit
+// half-cleaners serves every level).
 template <int G, bool PK>
 __device__ __forceinline__ void sort_group_t(uint32_t (&key)[kE], const uint32_t lane, const uint32_t g, const bool in_group, const PipeMul pm) {
     sort32_t<PK>(key, pm);
-    constexpr int NP = Geo<G>::NP;
-    if (NP >= 2) merge_level_t<G, 2, PK>(key, lane, g, in_group, pm);
-    if (NP >= 4) merge_level_t<G, 4, PK>(key, lane, g, in_group, pm);
-    if (NP >= 8) merge_level_t<G, 8, PK>(key, lane, g, in_group, pm);
-    if (NP >= 16) merge_level_t<G, 16, PK>(key, lane, g, in_group, pm);
-    if (NP >= 32) merge_level_t<G, 32, PK>(key, lane, g, in_group, pm);
+    constexpr uint32_t NP = (uint32_t)Geo<G>::NP;
+    if (NP < 2u) return;
+#pragma unroll 1
+    for (uint32_t ls = 2u; ls <= NP; ls <<= 1) {
+        xlane_t<G, true, PK>(key, ls - 1u, lane, g, in_group);
+#pragma unroll 1
+        for (uint32_t m = ls >> 2; m > 0u; m >>= 1) xlane_t<G, false, PK>(key, m, lane, g, in_group);
+        clean32_t<PK>(key, pm);
+    }
 }
 
 struct alignas(16) WarpSmem {  // one per warp: a warp runs on its own, no CTA-wide barrier anywhere
