@@ -118,7 +118,8 @@ struct Work {
     uint32_t n_parts;
     uint32_t *lit_list;              // rows holding a malformed interval (they take the literal heap sweep)
     uint32_t *bad_rows;              // one bit per row: the row holds a malformed interval (validate_kernel)
-    uint32_t *big_list;              // rows with k > kSmallMaxK
+    uint32_t *big_list;              // rows with k > kSmallMaxK that are sorted by a CTA
+    uint32_t *scan_list;             // rows with k > kSmallMaxK that are scanned by position (big_row_scans)
     uint32_t *huge_keys;             // event keys of rows beyond the shared-memory tier
 };
 
@@ -141,8 +142,8 @@ __global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Wor
         // were looked at) but its record is not valid: the sorting kernels skip it, literal_kernel computes it
         lit = (__ldg(w.bad_rows + (r >> 5)) >> (r & 31u)) & 1u;
         if (cls < 0 && !lit) {
-            const uint32_t j = atomicAdd(a.counters + kCntBigList, 1u);
-            w.big_list[j] = r;
+            if (big_row_scans(k, len)) w.scan_list[atomicAdd(a.counters + kCntScanList, 1u)] = r;
+            else w.big_list[atomicAdd(a.counters + kCntBigList, 1u)] = r;
         }
     }
     const uint32_t peers = __match_any_sync(FULL, cls);
@@ -448,7 +449,7 @@ __device__ void cta_row(const DetectArgs &a, const Work &w, uint32_t *cnt, uint3
 __global__ void __launch_bounds__(kCtaThreads) big_kernel(DetectArgs a, Work w, uint32_t c, uint32_t smem_words) {
     extern __shared__ __align__(16) uint32_t cta_smem[];
     __shared__ uint32_t sh[16];
-    const uint32_t n_big = min((uint32_t)a.rows.n_big, __ldcg(a.counters + kCntBigList));  // (rows redone by literal_kernel are not listed)
+    const uint32_t n_big = min((uint32_t)(a.rows.n_big - a.rows.n_scan), __ldcg(a.counters + kCntBigList));  // (rows redone by literal_kernel are not listed)
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
     for (uint32_t j = blockIdx.x; j < n_big; j += gridDim.x) {
@@ -464,6 +465,163 @@ __global__ void __launch_bounds__(kCtaThreads) big_kernel(DetectArgs a, Work w, 
         }
         if (wide) cta_row<false>(a, w, cnt, keys, r, c, sh);
         else cta_row<true>(a, w, cnt, keys, r, c, sh);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA tier, scan path (bigscan_kernel): a row with k > 512 whose read is short enough is not sorted. This is the heap
+// sweep of stack.rs:71-105 seen from the positions: cnt[x] counts the begins (low half) and the ends (high half) at
+// every position x of a window of the read (shared-memory atomics), a block scan gives the depth in front of every
+// thread's stretch of positions, and a walk over the stretch finds the crossings: at x the ends pop first
+// (stack.rs:72-81: a down-crossing when the depth falls from above c to c or less), then the begins push
+// (stack.rs:83-90: an up-crossing when it rises from c or less to above c) - a zero-length region (x, x) when both
+// happen. Work is O(len + k) instead of O(k log^2 k): a row of 5000 intervals takes a few microseconds of one CTA, two
+// CTAs per SM hide each other's load latencies. The crossings go to the staging buffer as the same pair list the
+// register tier writes (k + 1 pairs reserved up front: the ranks are only known window by window).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kScanThreads = kScanWindow / 32;  // one thread per 32 positions of a window
+static_assert(kScanThreads <= 1024 && kScanThreads % 32 == 0, "bigscan_kernel's block scan handles up to 32 warps");
+constexpr size_t kScanSmemBytes = (sizeof(uint32_t) + sizeof(uint16_t)) * kScanWindow;  // counters + the list of occupied positions
+
+__global__ void __launch_bounds__(kScanThreads, 2) bigscan_kernel(DetectArgs a, Work w, uint32_t c) {
+    // cnt_x[x]: begins | ends << 16 at position x of the window; occ[t]: which of positions 32 t .. 32 t + 31 hold anything;
+    // lst[]: the occupied positions, compacted, so that every thread walks an equal share of them (the events of a read
+    // crowd at its two ends: a thread per stretch of positions would leave one thread with all the work). Only occupied
+    // positions are ever looked at again (a read of 14 K bases holds a few thousand), and they are cleared on the way out,
+    // so nothing is zeroed per row.
+    extern __shared__ __align__(16) uint32_t cnt_x[];
+    uint16_t *lst = reinterpret_cast<uint16_t *>(cnt_x + kScanWindow);
+    __shared__ uint32_t occ[kScanThreads], s_w[32], s_v[4];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t ep = __ldcg(a.counters + kCntEpoch);
+    uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
+    const uint32_t n_scan = min((uint32_t)a.rows.n_scan, __ldcg(a.counters + kCntScanList));  // (rows redone by literal_kernel are not listed)
+    const uint32_t cc = min(c, 0x7FFFFFF0u);
+    for (uint32_t x = tid; x < kScanWindow; x += kScanThreads) cnt_x[x] = 0u;
+    occ[tid] = 0u;
+    if (tid < 32u) s_w[tid] = 0u;
+    auto block_excl = [&](uint32_t v, uint32_t *total) {  // exclusive scan of one value per thread
+        const uint32_t incl = warp_incl_scan(v);
+        __syncthreads();
+        if (lane == 31u) s_w[wid] = incl;
+        __syncthreads();
+        const uint32_t x = s_w[lane];  // (warps beyond the CTA's hold 0)
+        const uint32_t wi = warp_incl_scan(x);
+        *total = __shfl_sync(FULL, wi, 31);
+        return __shfl_sync(FULL, wi - x, wid) + incl - v;
+    };
+    // The next row's size, place and first intervals travel while this row is scanned (registers): a row is a chain of
+    // dependent loads otherwise (list entry -> row pointers -> intervals), paid by the whole CTA.
+    constexpr uint32_t NPF = 6;  // intervals per thread held ahead (rows of up to 3072 intervals entirely)
+    uint32_t r_n = 0, s_n = 0, k_n = 0, len_n = 0;
+    uint2 pf[NPF];
+    auto fetch_meta = [&](uint32_t jn) {
+        if (jn < n_scan) {
+            r_n = w.scan_list[jn];
+            s_n = a.rowptr[r_n];
+            k_n = a.rowptr[r_n + 1] - s_n;
+            len_n = a.len[r_n];
+        }
+    };
+    auto fetch_ivs = [&](uint32_t jn) {
+        if (jn < n_scan) {
+#pragma unroll
+            for (uint32_t u = 0; u < NPF; ++u)
+                if (tid + u * kScanThreads < k_n) pf[u] = __ldg(a.iv + s_n + tid + u * kScanThreads);
+        }
+    };
+    fetch_meta(blockIdx.x);
+    fetch_ivs(blockIdx.x);
+    for (uint32_t j = blockIdx.x; j < n_scan; j += gridDim.x) {
+        const uint32_t r = r_n, s = s_n, k = k_n, len = len_n;
+        const uint32_t n_pos = len + 1u;  // positions 0 .. len
+        if (tid == 0) s_v[2] = atomicAdd(cnt + kCntStage, k + 1u);  // the pair list P[q] = (D_{q-1}, U_q), q = 0 .. n_up <= k
+        uint32_t depth = 0, ups = 0, downs = 0;  // carried from window to window (the same in every thread)
+        for (uint32_t lo = 0; lo < n_pos; lo += kScanWindow) {
+            const uint32_t m = min(kScanWindow, n_pos - lo);
+            __syncthreads();  // the previous window is cleared
+            auto count = [&](const uint2 v) {
+                const uint32_t xb = v.x - lo, xe = v.y - lo;
+                if (xb < m) {
+                    atomicAdd(&cnt_x[xb], 1u);
+                    if (!(occ[xb >> 5] & (1u << (xb & 31u)))) atomicOr(&occ[xb >> 5], 1u << (xb & 31u));  // (a stale read costs an OR)
+                }
+                if (xe < m) {
+                    atomicAdd(&cnt_x[xe], 0x10000u);
+                    if (!(occ[xe >> 5] & (1u << (xe & 31u)))) atomicOr(&occ[xe >> 5], 1u << (xe & 31u));
+                }
+            };
+#pragma unroll
+            for (uint32_t u = 0; u < NPF; ++u)
+                if (tid + u * kScanThreads < k) count(pf[u]);
+            for (uint32_t i = tid + NPF * kScanThreads; i < k; i += kScanThreads) count(__ldg(a.iv + s + i));
+            if (lo + kScanWindow >= n_pos) {  // last window: the registers are free for the next row
+                fetch_meta(j + gridDim.x);
+            }
+            __syncthreads();
+            // compact the occupied positions (ascending), then thread t takes entries [e0, e1)
+            uint32_t n_occ;
+            {
+                const uint32_t bits = occ[tid];
+                uint32_t at = block_excl(__popc(bits), &n_occ);
+                for (uint32_t bm = bits; bm; bm &= bm - 1u) lst[at++] = (uint16_t)(32u * tid + __ffs(bm) - 1);
+                occ[tid] = 0u;
+            }
+            __syncthreads();
+            const uint32_t per = (n_occ + kScanThreads - 1u) / kScanThreads, e0 = min(tid * per, n_occ), e1 = min(e0 + per, n_occ);
+            uint32_t net = 0;
+            for (uint32_t e = e0; e < e1; ++e) {
+                const uint32_t q = cnt_x[lst[e]];
+                net += (q & 0xFFFFu) - (q >> 16);  // (wrapping u32: the sums are exact)
+            }
+            uint32_t net_all;
+            const uint32_t d0 = depth + block_excl(net, &net_all);  // depth in front of entry e0
+            auto walk = [&](auto on_up, auto on_down) {
+                uint32_t d = d0;
+                for (uint32_t e = e0; e < e1; ++e) {
+                    const uint32_t x = lst[e], q = cnt_x[x];
+                    const uint32_t ne = q >> 16, nb = q & 0xFFFFu;
+                    if (d > cc && d - ne <= cc) on_down(lo + x);  // (no end here: ne = 0, never true)
+                    d -= ne;
+                    if (d <= cc && d + nb > cc) on_up(lo + x);    // (no begin here: nb = 0, never true)
+                    d += nb;
+                }
+            };
+            uint32_t nu = 0, nd = 0, first_u = 0, last_d = 0;
+            walk([&](uint32_t x) { if (!nu) first_u = x; ++nu; }, [&](uint32_t x) { last_d = x; ++nd; });
+            uint32_t tot_ud;
+            const uint32_t r0 = block_excl(nu | (nd << 16), &tot_ud);
+            const uint32_t ru0 = ups + (r0 & 0xFFFFu), rd0 = downs + (r0 >> 16);
+            if (nu && ru0 == 0u) s_v[0] = first_u;                          // first up-crossing of the row
+            if (nd && (r0 >> 16) + nd == (tot_ud >> 16)) s_v[1] = last_d;   // last down-crossing so far
+            const uint32_t base = s_v[2];  // (written before the first barrier of the row)
+            if ((nu | nd) && (uint64_t)base + k + 1u <= w.stage_cap) {
+                uint32_t *P = reinterpret_cast<uint32_t *>(w.stage + base);
+                uint32_t ru = ru0, rd = rd0;
+                walk([&](uint32_t x) { P[2u * ru++ + 1u] = x; }, [&](uint32_t x) { P[2u * rd++ + 2u] = x; });
+            }
+            for (uint32_t e = e0; e < e1; ++e) cnt_x[lst[e]] = 0u;  // leave the window clean
+            if (lo + kScanWindow >= n_pos) fetch_ivs(j + gridDim.x);
+            depth += net_all;
+            ups += tot_ud & 0xFFFFu;
+            downs += tot_ud >> 16;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t base = s_v[2], n_up = ups, U0 = s_v[0], Dl = s_v[1];
+            if ((uint64_t)base + k + 1u <= w.stage_cap) {
+                uint32_t *P = reinterpret_cast<uint32_t *>(w.stage + base);
+                P[0] = 0u;
+                P[2u * n_up + 1u] = len;
+                const uint32_t q0 = n_up ? (U0 == 0u) : 0u;
+                const uint32_t ng = n_up ? n_up + (Dl != len) - q0 : (len != 0u);
+                w.meta[r] = make_uint2(base + q0, ng);
+            } else {
+                atomicAdd(cnt + kCntStageOverflow, 1u);
+                w.meta[r] = make_uint2(0u, 0u);
+            }
+        }
+        __syncthreads();  // s_v is reused by the next row
     }
 }
 
@@ -883,6 +1041,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint32_t *__restric
 __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ len,
                                                           uint32_t n_reads, DevRowStats *out) {
     __shared__ uint32_t s_cnt[kNumClasses + 1], s_max, s_bad[3];
+    (void)0;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * 1024u + tid;
     if (tid <= (uint32_t)kNumClasses) s_cnt[tid] = 0u;
     if (tid < 3u) s_bad[tid] = 0u;
@@ -900,8 +1059,14 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
             if (cls < 0) {  // big row: rare, straight to the global sums
                 cls = kNumClasses;
                 atomicAdd(&out->big_pairs, (unsigned long long)k + 1ull);
-                const unsigned long long hk = cta_words(k, l > kPackedMaxLen);
-                if (hk > kCtaMaxSmemWords) atomicAdd(&out->huge_keys, hk);
+                if (big_row_scans(k, l)) {
+                    atomicAdd(&out->n_scan, 1u);
+                    atomicMax(&out->max_len_scan, l);
+                } else {
+                    atomicMax(&out->max_k_sort, k);
+                    const unsigned long long hk = cta_words(k, l > kPackedMaxLen);
+                    if (hk > kCtaMaxSmemWords) atomicAdd(&out->huge_keys, hk);
+                }
             }
             if (l > kPackedMaxLen) atomicAdd(&s_bad[2], 1u);
         }
@@ -1112,6 +1277,7 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, size_t *tota
     w.stage = reinterpret_cast<uint2 *>(take(sizeof(uint2) * ((size_t)w.stage_cap + 1)));
     w.part_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * ((size_t)w.n_parts + 8)));
     w.big_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
+    w.scan_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.huge_keys = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (huge_keys + 1)));
     w.lit_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)a.n_reads + 1)));
     w.bad_rows = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)a.n_reads / 32 + 2)));
@@ -1165,6 +1331,7 @@ const DevCfg *dev_cfg() {
         int sm = 0, occ = 0;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return;
         if (cudaFuncSetAttribute(big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCtaMaxSmemWords * sizeof(uint32_t))) != cudaSuccess) return;
+        if (cudaFuncSetAttribute(bigscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes) != cudaSuccess) return;
         if (cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_kernel, kSortThreads, kSortSmemBytes) != cudaSuccess || occ < 1) return;
         d.n_sm = sm;
@@ -1231,21 +1398,30 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
     bool forked = false;
     if (a.rows.n_big) {
         // the few rows with more than 512 intervals (CTA tier) run on a side stream, beside the register tier (both only
-        // append to the staging buffer); shared memory for the largest row (wide if any read is); rows beyond
-        // kCtaMaxSmemWords sort in a global slab
+        // append to the staging buffer)
         forked = a.side_stream && a.ev_fork && a.ev_join && cudaEventRecord(a.ev_fork, stream) == cudaSuccess &&
                  cudaStreamWaitEvent(a.side_stream, a.ev_fork, 0) == cudaSuccess;
-        uint64_t words = cta_words(a.max_k, a.rows.n_wide != 0);
+        if (a.rows.n_scan) {  // short enough reads: begins and ends counted per position, depth scanned window by window
+            uint32_t grid = 2u * (uint32_t)dc->n_sm;
+            if (grid > a.rows.n_scan) grid = (uint32_t)a.rows.n_scan;
+            bigscan_kernel<<<grid, kScanThreads, kScanSmemBytes, forked ? a.side_stream : stream>>>(a, w, coverage);
+            ++launches;
+        }
+    }
+    if (a.rows.n_big > a.rows.n_scan) {
+        // the others are sorted: shared memory for the largest row (wide if any read is); rows beyond kCtaMaxSmemWords
+        // sort in a global slab
+        uint64_t words = cta_words(a.rows.max_k_sort, a.rows.n_wide != 0);
         if (words > kCtaMaxSmemWords) words = kCtaMaxSmemWords;
         uint32_t per_sm = (uint32_t)((220u * 1024u) / (words * 4u + 1024u));
         if (per_sm < 1u) per_sm = 1u;
         if (per_sm > 8u) per_sm = 8u;
         uint32_t grid = (uint32_t)dc->n_sm * per_sm;
-        if (grid > a.rows.n_big) grid = (uint32_t)a.rows.n_big;
+        if (grid > a.rows.n_big - a.rows.n_scan) grid = (uint32_t)(a.rows.n_big - a.rows.n_scan);
         big_kernel<<<grid, kCtaThreads, words * sizeof(uint32_t), forked ? a.side_stream : stream>>>(a, w, coverage, (uint32_t)words);
         ++launches;
-        if (forked && cudaEventRecord(a.ev_join, a.side_stream) != cudaSuccess) return -1;
     }
+    if (forked && cudaEventRecord(a.ev_join, a.side_stream) != cudaSuccess) return -1;
     {
         const ClassTab tab = make_plan(a);
         const uint32_t items = tab.item_base[kNumClasses];

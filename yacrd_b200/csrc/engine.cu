@@ -827,6 +827,9 @@ int yb_upload(yb_ctx *c) {
         if (ds.bad_len) return c->fail(YB_ERR_TOO_LARGE, "%u read(s) are longer than 2^31-1 bases", ds.bad_len);
         yb::RowStats rs;
         rs.n_big = ds.n_big;
+        rs.n_scan = ds.n_scan;
+        rs.max_len_scan = ds.max_len_scan;
+        rs.max_k_sort = ds.max_k_sort;
         rs.big_pairs = ds.big_pairs;
         rs.huge_keys = ds.huge_keys;
         rs.n_wide = ds.n_wide;

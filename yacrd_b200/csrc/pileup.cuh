@@ -36,6 +36,7 @@ constexpr uint32_t kHistSlots = 32;
 constexpr uint32_t kCntEpoch = 2 * kNumCounters;          // number of detect steps finished on this buffer
 constexpr uint32_t kCntBigList = 2 * kNumCounters + 1;    // upload: rows with more than 512 intervals (big tier)
 constexpr uint32_t kCntLiteralList = 2 * kNumCounters + 2;  // upload: rows with a malformed interval
+constexpr uint32_t kCntScanList = 2 * kNumCounters + 4;     // upload: big rows of the position-scan path
 constexpr uint32_t kCntPeerTimeoutWait = 2 * kNumCounters + 3;  // peer_wait_kernel gave up (a rank died or never launched)
 constexpr uint32_t kCntClassCursor = 2 * kNumCounters + 8;  // upload: kNumClasses cursors of the worklist scatter
 constexpr uint32_t kCounterWords = 2 * kNumCounters + 8 + 24;
@@ -74,6 +75,14 @@ __host__ __device__ constexpr int class_lanes_c(int gi) {
 constexpr uint32_t kPackedMaxLen = 65534u;
 constexpr uint32_t kRegisterTierMaxK = 512u;
 
+// A big row (k > 512) is not sorted at all when its read is short enough: its begins and ends are counted per position in
+// shared memory (16-bit counts) and the depth is scanned over the read's length, a window of kScanWindow positions at a
+// time (4 bytes per position; at most kScanMaxWindows windows, beyond that sorting is cheaper).
+constexpr uint32_t kScanWindow = 16384u, kScanMaxWindows = 24u, kScanMaxK = 65534u;
+__host__ __device__ inline bool big_row_scans(uint32_t k, uint32_t len) {
+    return k <= kScanMaxK && len < kScanWindow * kScanMaxWindows;
+}
+
 // Size class of a row, or -1 for a big row (k > 512).
 __host__ __device__ inline int class_of_row(uint32_t k, uint32_t len) {
     if (k > kRegisterTierMaxK) return -1;
@@ -84,7 +93,10 @@ __host__ __device__ inline int class_of_row(uint32_t k, uint32_t len) {
 
 // What the host knows about the rows at freeze time (sizes the scratch exactly).
 struct RowStats {
-    uint64_t n_big = 0;      // rows with k > 512 (big tier)
+    uint64_t n_big = 0;      // rows with k > 512 (big tier), those of the scan path included
+    uint64_t n_scan = 0;     // big rows that take the position-scan path (big_row_scans)
+    uint32_t max_len_scan = 0;  // longest of them
+    uint32_t max_k_sort = 0;    // largest row of the sort path of the big tier
     uint64_t big_pairs = 0;  // sum over them of k + 1
     uint64_t huge_keys = 0;  // sum over rows beyond the shared-memory tier of next_pow2(2k)
     uint64_t n_wide = 0;     // rows longer than kPackedMaxLen (positions do not fit 16 bits)
@@ -126,6 +138,7 @@ struct DetectArgs {
 struct DevRowStats {
     uint32_t class_count[kNumClasses];
     uint32_t n_big, n_wide, max_k;
+    uint32_t n_scan, max_len_scan, max_k_sort, pad0_;
     uint32_t bad_rowptr;           // rows with rowptr[r + 1] < rowptr[r]
     uint32_t bad_len;              // rows longer than kMaxLength
     uint32_t pad_;
