@@ -10,8 +10,27 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.gpu
+def test_peer_allgather_one_gpu_per_rank():
+    """The same over NVLink peer memory: needs two visible GPUs, and says so when it cannot run (a record that only shows
+    the shared-GPU variant below has not exercised peer stores)."""
+    if _device_count() < 2:
+        pytest.skip("only %d GPU visible: the peer-memory all-gather over NVLink is not exercised by this run "
+                    "(bench.py --gpus N checks the gathered bitmap against the oracle on multi-GPU boxes)" % _device_count())
+    _run_two_ranks(expect="one GPU per rank")
+
+
 @pytest.mark.gpu
 def test_peer_allgather_two_ranks():
+    _run_two_ranks()
+
+
+def _run_two_ranks(expect=None):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -28,3 +47,5 @@ def test_peer_allgather_two_ranks():
         outs.append(out)
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and ("rank %d ok" % r) in out, out[-3000:]
+        if expect:
+            assert expect in out, out[-3000:]

@@ -1089,54 +1089,88 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
     }
 }
 
-// validate_kernel (upload time): 0 <= begin < end <= length for every interval. A warp takes 32 consecutive rows and
-// walks each of them with coalesced loads. Rows that hold a malformed interval go to a list: the closed form of the
-// sorting kernels is only equal to the reference's heap sweep for well-formed rows, so those rows are redone by
-// literal_kernel (the reference accepts such input and gives a deterministic answer, stack.rs:61-139).
+// validate_kernel (upload time): 0 <= begin < end <= length for every interval. The interval buffer is cut into chunks
+// of kValidateChunk intervals whatever the rows look like (a read with 5000 intervals is not one warp's problem); a warp
+// finds the row its chunk starts in (binary search in the row pointers), then streams the chunk 32 intervals at a time
+// (coalesced, the next step's load already in flight) and finds each interval's row from a window of 32 row ends held by
+// the lanes. Rows that hold a malformed interval are flagged and listed: the closed form of the sorting kernels is only
+// equal to the reference's heap sweep for well-formed rows, so those rows are computed by literal_kernel (the reference
+// accepts such input and gives a deterministic answer, stack.rs:61-139).
+constexpr uint32_t kValidateChunk = 8192;
+
 __global__ void __launch_bounds__(256) validate_kernel(const uint2 *__restrict__ iv, const uint32_t *__restrict__ rowptr,
-                                                       const uint32_t *__restrict__ len, uint32_t n_reads, DevRowStats *out,
+                                                       const uint32_t *__restrict__ len, uint32_t n_reads, uint32_t n_iv, DevRowStats *out,
                                                        uint32_t *lit_list, uint32_t *lit_count, uint32_t *bad_row_bits) {
     const uint32_t lane = lane_id(), warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n_chunks = (n_iv + kValidateChunk - 1u) / kValidateChunk;
+    const uint4 *iv4 = reinterpret_cast<const uint4 *>(iv);  // two intervals per load (chunks start at even intervals)
     uint32_t bad = 0, bad_rows = 0;
-    for (uint32_t r0 = warp * 32u; r0 < n_reads; r0 += n_warps * 32u) {
-        // the 32 rows are one contiguous stretch [P0, P1) of the interval buffer: the warp streams it 32 intervals at a
-        // time (coalesced, the next step's load already in flight) and finds each interval's row from the row ends the
-        // lanes hold (a row ends inside a step of 32 about every other step)
-        const uint32_t r = min(r0 + lane, n_reads - 1u);
-        const uint32_t p1 = __ldg(rowptr + r + 1), l = __ldg(len + r);
-        const uint32_t P0 = __ldg(rowptr + r0), P1 = __shfl_sync(FULL, p1, 31);
-        uint32_t word = 0, cur = 0;  // bit j: row r0 + j holds a malformed interval; cur: first row that ends behind the last step
-        uint2 v = make_uint2(0u, 1u);
-        if (P0 + lane < P1) v = __ldg(iv + P0 + lane);
-        for (uint32_t base = P0; base < P1; base += 32u) {
-            const uint32_t i = base + lane;
-            const uint2 vc = v;
-            if (i + 32u < P1) v = __ldg(iv + i + 32u);
-            uint32_t row = cur, rr = cur;
-            for (; rr < 32u; ++rr) {  // rows that end inside this step (uniform loop)
-                const uint32_t e = __shfl_sync(FULL, p1, rr);
-                if (e > base + 31u) break;
-                row += e <= i;
+    for (uint32_t ch = warp; ch < n_chunks; ch += n_warps) {
+        const uint32_t P0 = ch * kValidateChunk, P1 = min(P0 + kValidateChunk, n_iv);
+        uint32_t r0;  // the row interval P0 lies in: the last row whose first interval is at or before P0
+        {
+            uint32_t lo = 0, hi = n_reads;  // rowptr[lo] <= P0 < rowptr[hi]
+            while (hi - lo > 1u) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(rowptr + mid) <= P0) lo = mid;
+                else hi = mid;
             }
-            cur = rr;
-            const uint32_t lj = __shfl_sync(FULL, l, min(row, 31u));
-            if (i < P1 && !(vc.x < vc.y && vc.y <= lj)) {
-                ++bad;
-                word |= 1u << row;
-            }
+            r0 = lo;
         }
-        word = __reduce_or_sync(FULL, word);
-        if (lane == 0) bad_row_bits[r0 >> 5] = word;
-        if (word) {  // rare
-            bad_rows += __popc(word);
-            if (lane == 0) {
-                const uint32_t at = atomicAdd(lit_count, (uint32_t)__popc(word));
-                uint32_t q = 0;
-                for (uint32_t m = word; m; m &= m - 1u) lit_list[at + q++] = r0 + (uint32_t)__ffs(m) - 1u;
+        // window of 32 rows from r0: lane j holds the end and the length of row r0 + j
+        uint32_t p1 = __ldg(rowptr + min(r0 + lane, n_reads - 1u) + 1u), l = __ldg(len + min(r0 + lane, n_reads - 1u));
+        // (the window behind it is already on its way: moving on must not wait for memory)
+        uint32_t p1n = __ldg(rowptr + min(r0 + 32u + lane, n_reads - 1u) + 1u), ln = __ldg(len + min(r0 + 32u + lane, n_reads - 1u));
+        uint32_t rr = 0;  // first row of the window that ends behind the last step
+        const uint4 none = make_uint4(0u, 1u, 0u, 1u);
+        auto load2 = [&](uint32_t i) {  // intervals i, i + 1 (i even); beyond the buffer's last interval: a well-formed dummy
+            if (i + 1u < n_iv) return __ldg(iv4 + (i >> 1));
+            uint4 x = none;
+            if (i < n_iv) {
+                const uint2 y = __ldg(iv + i);
+                x.x = y.x, x.y = y.y;
             }
+            return x;
+        };
+        uint4 va = P0 + 2u * lane < P1 ? load2(P0 + 2u * lane) : none, vb = P0 + 64u + 2u * lane < P1 ? load2(P0 + 64u + 2u * lane) : none;
+        for (uint32_t base = P0; base < P1; base += 64u) {
+            const uint32_t i0 = base + 2u * lane;
+            const uint4 vc = va;
+            va = vb;
+            vb = i0 + 128u < P1 ? load2(i0 + 128u) : none;
+            uint32_t l0 = 0, l1 = 0, row0 = 0, row1 = 0;
+            bool f0 = false, f1 = false;
+            for (;;) {  // rows that end inside this step (uniform loop; the window moves on when it is used up)
+                if (rr == 32u) {
+                    r0 += 32u;
+                    p1 = p1n;
+                    l = ln;
+                    p1n = __ldg(rowptr + min(r0 + 32u + lane, n_reads - 1u) + 1u);
+                    ln = __ldg(len + min(r0 + 32u + lane, n_reads - 1u));
+                    rr = 0u;
+                }
+                const uint32_t e = __shfl_sync(FULL, p1, rr), le = __shfl_sync(FULL, l, rr);
+                if (!f0 && i0 < e) f0 = true, l0 = le, row0 = r0 + rr;
+                if (!f1 && i0 + 1u < e) f1 = true, l1 = le, row1 = r0 + rr;
+                if (e > base + 63u || r0 + rr + 1u >= n_reads) break;  // this row goes on behind the step (or is the last one)
+                ++rr;
+            }
+            auto check = [&](uint32_t i, uint32_t b, uint32_t e, uint32_t lj, uint32_t row) {
+                if (i < P1 && !(b < e && e <= lj)) {
+                    ++bad;
+                    const uint32_t bit = 1u << (row & 31u);
+                    if (!(atomicOr(bad_row_bits + (row >> 5), bit) & bit)) {
+                        lit_list[atomicAdd(lit_count, 1u)] = row;
+                        ++bad_rows;
+                    }
+                }
+            };
+            check(i0, vc.x, vc.y, l0, row0);
+            check(i0 + 1u, vc.z, vc.w, l1, row1);
         }
     }
     bad = warp_sum(bad);
+    bad_rows = warp_sum(bad_rows);
     if (lane == 0 && bad) {
         atomicAdd(&out->malformed, bad);
         atomicAdd(&out->malformed_rows, bad_rows);
@@ -1364,10 +1398,11 @@ int launch_upload_kernels(const DetectArgs &a, DevRowStats *out, cudaStream_t st
     Work w = carve(a, a.rows.huge_keys, a.rows.n_big, &total);
     if (total > a.scratch_bytes) return -1;
     uint32_t grid = (uint32_t)dc->n_sm * 8u;
-    const uint32_t want = (a.n_reads + 255u) / 256u;
-    if (grid > want) grid = want;
+    const uint32_t want = ((a.n_iv + kValidateChunk - 1u) / kValidateChunk + 7u) / 8u;  // one chunk per warp, 8 warps per CTA
+    if (grid > want) grid = std::max(want, 1u);
     if (cudaMemsetAsync(w.part_desc, 0, sizeof(unsigned long long) * (size_t)w.n_parts, stream) != cudaSuccess) return -1;
-    validate_kernel<<<grid, 256, 0, stream>>>(a.iv, a.rowptr, a.len, a.n_reads, out, w.lit_list, a.counters + kCntLiteralList, w.bad_rows);
+    if (cudaMemsetAsync(w.bad_rows, 0, sizeof(uint32_t) * ((size_t)a.n_reads / 32 + 1), stream) != cudaSuccess) return -1;
+    if (a.n_iv) validate_kernel<<<grid, 256, 0, stream>>>(a.iv, a.rowptr, a.len, a.n_reads, a.n_iv, out, w.lit_list, a.counters + kCntLiteralList, w.bad_rows);
     scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, make_plan(a));
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
