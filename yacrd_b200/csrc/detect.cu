@@ -66,12 +66,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
     return v;
 }
 
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
-    return v;
-}
-
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // ------------------------------------------------------------------------------------------------
@@ -89,11 +83,16 @@ constexpr uint32_t kSortThreads = kSortWarps * 32;
 #endif
 constexpr uint32_t kBufIntervals = YB_BUF_INTERVALS;  // row slots of a warp's slab buffer: a batch of class G holds min(floor(32 / G),
                                                       // floor(kBufIntervals / (kE G + 2))) rows; 32 (kE + 2) = 32 rows of the G = 1 class
+constexpr uint32_t kValidateChunk = 4096;      // intervals per CTA of validate_kernel
 constexpr uint32_t kScatterRows = 1024;        // rows per CTA of scatter_kernel
 #ifndef YB_ORDER_THREADS
 #define YB_ORDER_THREADS 256
 #endif
-constexpr uint32_t kOrderThreads = YB_ORDER_THREADS, kOrderRows = 4, kPartRows = kOrderThreads * kOrderRows;  // rows per CTA of order_kernel
+#ifndef YB_ORDER_ROWS
+#define YB_ORDER_ROWS 4
+#endif
+constexpr uint32_t kOrderThreads = YB_ORDER_THREADS, kOrderRows = YB_ORDER_ROWS, kPartRows = kOrderThreads * kOrderRows;  // rows per CTA of order_kernel
+static_assert(kOrderRows == 1 || kOrderRows == 2 || kOrderRows == 4, "order_kernel: 1, 2 or 4 rows per thread");
 constexpr uint32_t kStageChunk = 2048;       // pairs a warp reserves in the staging buffer per atomic (an L2 round trip the warp waits for)
 constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
 
@@ -114,7 +113,8 @@ struct Work {
     uint2 *meta;                     // n_reads: {where the row's bad regions sit in `stage` (pairs), how many}
     uint2 *stage;                    // bad regions in batch-completion order (warps reserve chunks with one atomic)
     uint32_t stage_cap;              // pairs
-    unsigned long long *part_desc;   // n_parts: step tag << 32 | bad regions of the part (order_kernel publishes, later parts sum)
+    uint32_t *part_total;            // n_parts: bad regions of every part of kPartRows rows (totals_kernel)
+    uint32_t *part_prefix;           // their exclusive prefix (the last CTA of totals_kernel)
     uint32_t n_parts;
     uint32_t *lit_list;              // rows holding a malformed interval (they take the literal heap sweep)
     uint32_t *bad_rows;              // one bit per row: the row holds a malformed interval (validate_kernel)
@@ -802,33 +802,64 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
 constexpr size_t kSortSmemBytes = kWarpSmemBytes * kSortWarps;
 
 // ------------------------------------------------------------------------------------------------
-// ordering pass (order_kernel, the second and last kernel of a detect step): the sorting kernels left, per row, a
-// staging offset and a count. A CTA takes one part of 2048 rows (in ticket order), 4 consecutive rows per thread: it
-// publishes the part's total in one 64-bit word tagged with the step number (never reset) as soon as its counts are
-// loaded, sums the totals of ALL parts before it (a thousand words at most; it only ever waits for parts that are
-// already running and whose total does not depend on anybody: no scan kernel, no look-back chain, and no RED per row
-// in the sorting kernels, which serialised in L2 when every warp of the GPU worked on the same stretch of rows), turns
-// counts into offsets (thread-local prefix + block scan), moves the staged regions to their final place, classifies
-// (editor/mod.rs:85-100) and writes the 2-bit bitmap (to every peer's gather buffer when the all-gather is fused in).
-// The last CTA to finish closes the step: it zeroes the other counter set, bumps the step number and, with peers, tells
-// every rank that this rank's slot is complete.
+// ordering pass: the sorting kernels left, per row, a staging offset and a count. totals_kernel sums the counts of every
+// part of 1024 rows (one warp per part: a few microseconds; a RED per row from the sorting kernels would serialise in L2,
+// because at any moment every warp of the GPU works on the same stretch of rows). order_kernel then takes one part per
+// CTA, 4 consecutive rows per thread, with no ordering between CTAs: it sums the totals of the parts before it (at most
+// a couple of thousand words), turns counts into offsets (thread-local prefix + block scan), moves the staged regions to
+// their final place, classifies (editor/mod.rs:85-100) and writes the 2-bit bitmap (to every peer's gather buffer when
+// the all-gather is fused in). The CTA of the last part closes the step once the others are through: it zeroes the other
+// counter set, bumps the step number and, with peers, tells every rank that this rank's slot is complete.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__global__ void __launch_bounds__(256) totals_kernel(DetectArgs a, Work w) {
+    __shared__ uint32_t s_last, s_w[8];
+    const uint32_t tid = threadIdx.x, lane = lane_id(), wid = tid >> 5, part = (blockIdx.x * blockDim.x + tid) >> 5;
+    const uint32_t ep = __ldcg(a.counters + kCntEpoch);
+    uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
+    if (part < w.n_parts) {
+        const uint32_t r0 = part * kPartRows, r1 = min(r0 + kPartRows, a.n_reads);
+        uint32_t sum = 0;
+        for (uint32_t r = r0 + 2u * lane; r < r1; r += 64u) {  // two 8-byte records per load
+            if (r + 1u < r1) {
+                const uint4 x = *reinterpret_cast<const uint4 *>(w.meta + r);
+                sum += x.y + x.w;
+            } else {
+                sum += w.meta[r].y;
+            }
+        }
+        sum = __reduce_add_sync(FULL, sum);
+        if (lane == 0) w.part_total[part] = sum;
+    }
+    // the last CTA out turns the totals into their exclusive prefix (order_kernel's CTAs read one word each)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(cnt + kCntTotalsDone, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const uint32_t n = w.n_parts, per = (n + 255u) / 256u, beg = min(tid * per, n), end = min(beg + per, n);
+    uint32_t s = 0;
+    for (uint32_t i = beg; i < end; ++i) s += __ldcg(w.part_total + i);
+    const uint32_t incl = warp_incl_scan(s);
+    if (lane == 31u) s_w[wid] = incl;
+    __syncthreads();
+    uint32_t run = incl - s;
+#pragma unroll
+    for (uint32_t q = 0; q < 8u; ++q) run += q < wid ? s_w[q] : 0u;
+    for (uint32_t i = beg; i < end; ++i) {
+        const uint32_t t = __ldcg(w.part_total + i);
+        w.part_prefix[i] = run;
+        run += t;
+    }
 }
 
 __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_kernel(DetectArgs a, Work w, double not_cov) {
     constexpr uint32_t R = kOrderRows, NW = kOrderThreads / 32;
-    __shared__ uint32_t s_warp[NW], s_pre[NW], s_hist[NW], s_last, s_part;
+    __shared__ uint32_t s_warp[NW], s_hist[NW];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
-    if (tid == 0) s_part = atomicAdd(cnt + kCntTicket, 1u);  // parts start in ticket order: a part only waits for parts that run
+    const uint32_t part = blockIdx.x, r0 = part * kPartRows + tid * R;
     uint32_t peer_step = 0;
     if (a.n_peers) {
         // every rank has finished step peer_step - 1 (and, in its stream order, whatever read the gather buffer of step
@@ -845,25 +876,30 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
             if ((int32_t)(seen - peer_step) < 0) atomicAdd(cnt + kCntPeerTimeout, 1u);
         }
     }
-    __syncthreads();
-    const uint32_t part = s_part, r0 = part * kPartRows + tid * R;
     // everything the rows need is requested up front; the first two regions of a row (most have <= 3) ride along
+    const uint32_t pre = __ldg(w.part_prefix + part);  // regions of the parts before this one
     uint2 m[R];
     uint32_t l[R];
     const bool full = r0 + R <= a.n_reads;
     if (full) {
-        const uint4 *mp = reinterpret_cast<const uint4 *>(w.meta + r0);
-        const uint4 *lp = reinterpret_cast<const uint4 *>(a.len + r0);
+        if (R == 1) {
+            m[0] = w.meta[r0];
+            l[0] = __ldg(a.len + r0);
+        } else {
+            const uint4 *mp = reinterpret_cast<const uint4 *>(w.meta + r0);
 #pragma unroll
-        for (uint32_t i = 0; i < R / 2; ++i) {
-            const uint4 x = mp[i];
-            m[2 * i] = make_uint2(x.x, x.y);
-            m[2 * i + 1] = make_uint2(x.z, x.w);
-        }
-#pragma unroll
-        for (uint32_t i = 0; i < R / 4; ++i) {
-            const uint4 x = __ldg(lp + i);
-            l[4 * i] = x.x, l[4 * i + 1] = x.y, l[4 * i + 2] = x.z, l[4 * i + 3] = x.w;
+            for (uint32_t i = 0; i < R / 2; ++i) {
+                const uint4 x = mp[i];
+                m[2 * i] = make_uint2(x.x, x.y);
+                m[(2 * i + 1) % R] = make_uint2(x.z, x.w);
+            }
+            if (R == 2) {
+                const uint2 x = __ldg(reinterpret_cast<const uint2 *>(a.len + r0));
+                l[0] = x.x, l[1 % R] = x.y;
+            } else {
+                const uint4 x = __ldg(reinterpret_cast<const uint4 *>(a.len + r0));
+                l[0] = x.x, l[1 % R] = x.y, l[2 % R] = x.z, l[3 % R] = x.w;
+            }
         }
     } else {
 #pragma unroll
@@ -886,25 +922,9 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
     const uint32_t incl = warp_incl_scan(mine);
     if (lane == 31u) s_warp[wid] = incl;
     __syncthreads();
-    const unsigned long long tag = (unsigned long long)(ep + 1u) << 32;
-    if (tid == 0) {  // the part's total, for the parts behind this one
-        uint32_t tot = 0;
+    uint32_t gp = pre + incl - mine;
 #pragma unroll
-        for (uint32_t q = 0; q < NW; ++q) tot += s_warp[q];
-        st_desc(w.part_desc + part, tag | tot);
-    }
-    uint32_t pre = 0;  // totals of the parts before this one (they hold earlier tickets: running or done)
-    for (uint32_t i = tid; i < part; i += kOrderThreads) {
-        unsigned long long d = ld_desc(w.part_desc + i);
-        while ((d >> 32) != (tag >> 32)) d = ld_desc(w.part_desc + i);
-        pre += (uint32_t)d;
-    }
-    pre = __reduce_add_sync(FULL, pre);
-    if (lane == 0u) s_pre[wid] = pre;
-    __syncthreads();
-    uint32_t gp = incl - mine;
-#pragma unroll
-    for (uint32_t q = 0; q < NW; ++q) gp += s_pre[q] + (q < wid ? s_warp[q] : 0u);
+    for (uint32_t q = 0; q < NW; ++q) gp += q < wid ? s_warp[q] : 0u;
     if (tid == kOrderThreads - 1u && part == w.n_parts - 1u) a.gap_ptr[a.n_reads] = gp + mine;
     uint32_t off[R], cl[R], h1 = 0, h2 = 0, bits = 0;
 #pragma unroll
@@ -934,12 +954,9 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
         h2 += cl[i] == 2u;
         bits |= cl[i] << (2u * i);
     }
-    if (full) {
-        uint4 *gpp = reinterpret_cast<uint4 *>(a.gap_ptr + r0);
-#pragma unroll
-        for (uint32_t i = 0; i < R / 4; ++i) gpp[i] = make_uint4(off[4 * i], off[4 * i + 1], off[4 * i + 2], off[4 * i + 3]);
-        static_assert(R == 4, "class codes of a thread's rows go out as one 4-byte store");
-        *reinterpret_cast<uint32_t *>(a.cls + r0) = cl[0] | cl[1] << 8 | cl[2] << 16 | cl[3] << 24;
+    if (full && R == 4) {
+        *reinterpret_cast<uint4 *>(a.gap_ptr + r0) = make_uint4(off[0], off[1 % R], off[2 % R], off[3 % R]);
+        *reinterpret_cast<uint32_t *>(a.cls + r0) = cl[0] | cl[1 % R] << 8 | cl[2 % R] << 16 | cl[3 % R] << 24;
     } else {
 #pragma unroll
         for (uint32_t i = 0; i < R; ++i)
@@ -948,11 +965,12 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
                 a.cls[r0 + i] = (uint8_t)cl[i];
             }
     }
-    // four threads (16 rows) make one 32-bit word of the 2-bit bitmap
-    uint32_t word = bits << (8u * (lane & 3u));
-    word |= __shfl_xor_sync(FULL, word, 1);
-    word |= __shfl_xor_sync(FULL, word, 2);
-    if ((lane & 3u) == 0u && r0 < a.n_reads) {
+    // 16 / R threads (16 rows) make one 32-bit word of the 2-bit bitmap
+    constexpr uint32_t TPW = 16u / R;
+    uint32_t word = bits << (2u * R * (lane & (TPW - 1u)));
+#pragma unroll
+    for (uint32_t o = 1; o < TPW; o <<= 1) word |= __shfl_xor_sync(FULL, word, o);
+    if ((lane & (TPW - 1u)) == 0u && r0 < a.n_reads) {
         if (a.n_peers == 0u) {
             reinterpret_cast<uint32_t *>(a.bitmap)[r0 >> 4] = word;
         } else {  // all-gather fused into the epilogue: the word goes to this rank's slot on every rank (NVLink stores);
@@ -976,21 +994,34 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
         if (n_live - c1 - c2) atomicAdd(slot + 0, n_live - c1 - c2);
         if (c1) atomicAdd(slot + 1, c1);
         if (c2) atomicAdd(slot + 2, c2);
-        __threadfence();
-        s_last = atomicAdd(cnt + kCntDone, 1u) == w.n_parts - 1u;
     }
-    __syncthreads();
-    if (s_last) {  // the step is complete: next step's counter set, step number, peers
-        uint32_t *other = a.counters + ((ep + 1u) & 1u) * kNumCounters;
-        for (uint32_t i = tid; i < kNumCounters; i += kOrderThreads) other[i] = 0u;
+    // the CTA of the last part closes the step once every other CTA is through (they leave one RED behind and go): next
+    // step's counter set, step number, peers
+    if (part != w.n_parts - 1u) {
         __threadfence();
         __syncthreads();
-        if (tid == 0) a.counters[kCntEpoch] = ep + 1u;
-        if (a.n_peers) {
-            __threadfence_system();  // every part's peer stores (fenced by their writers before kCntDone) before the flags
-            if (tid < a.n_peers) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flag[tid] + a.rank), "r"(peer_step + 1u) : "memory");
-            if (tid == 0) a.peer_flag[a.rank][31] = peer_step + 1u;
+        if (tid == 0) atomicAdd(cnt + kCntDone, 1u);
+        return;
+    }
+    if (tid == 0) {
+        uint32_t seen = 0;
+        for (uint32_t spin = 0; spin < (1u << 24); ++spin) {  // bounded: a CTA that died must not hang the GPU
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt + kCntDone) : "memory");
+            if (seen >= w.n_parts - 1u) break;
+            __nanosleep(100);
         }
+        if (seen < w.n_parts - 1u) atomicAdd(a.counters + kCntOrderTimeout, 1u);
+    }
+    __syncthreads();
+    uint32_t *other = a.counters + ((ep + 1u) & 1u) * kNumCounters;
+    for (uint32_t i = tid; i < kNumCounters; i += kOrderThreads) other[i] = 0u;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) a.counters[kCntEpoch] = ep + 1u;
+    if (a.n_peers) {
+        __threadfence_system();  // every part's peer stores (fenced by their writers before kCntDone) before the flags
+        if (tid < a.n_peers) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flag[tid] + a.rank), "r"(peer_step + 1u) : "memory");
+        if (tid == 0) a.peer_flag[a.rank][31] = peer_step + 1u;
     }
 }
 
@@ -1039,7 +1070,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint32_t *__restric
 // row_stats_kernel (upload time): size-class histogram, big-row scratch needs, input sanity
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ len,
-                                                          uint32_t n_reads, DevRowStats *out) {
+                                                          uint32_t n_reads, DevRowStats *out, uint32_t *chunk_row) {
     __shared__ uint32_t s_cnt[kNumClasses + 1], s_max, s_bad[3];
     (void)0;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * 1024u + tid;
@@ -1055,6 +1086,8 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
             atomicAdd(&s_bad[0], 1u);
         } else {
             k = p1 - p0;
+            // validate_kernel cuts the interval buffer into chunks of kValidateChunk: the row a chunk starts in
+            for (uint32_t ch = (p0 + kValidateChunk - 1u) / kValidateChunk; k && (uint64_t)ch * kValidateChunk < p1; ++ch) chunk_row[ch] = r;
             cls = class_of_row(k, l);
             if (cls < 0) {  // big row: rare, straight to the global sums
                 cls = kNumClasses;
@@ -1090,90 +1123,93 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
 }
 
 // validate_kernel (upload time): 0 <= begin < end <= length for every interval. The interval buffer is cut into chunks
-// of kValidateChunk intervals whatever the rows look like (a read with 5000 intervals is not one warp's problem); a warp
-// finds the row its chunk starts in (binary search in the row pointers), then streams the chunk 32 intervals at a time
-// (coalesced, the next step's load already in flight) and finds each interval's row from a window of 32 row ends held by
-// the lanes. Rows that hold a malformed interval are flagged and listed: the closed form of the sorting kernels is only
-// equal to the reference's heap sweep for well-formed rows, so those rows are computed by literal_kernel (the reference
-// accepts such input and gives a deterministic answer, stack.rs:61-139).
-constexpr uint32_t kValidateChunk = 8192;
+// of kValidateChunk intervals whatever the rows look like (a read with 5000 intervals is not one thread's problem). A CTA
+// takes a chunk: row_stats_kernel left the row every chunk starts in, so the CTA copies the row pointers and lengths of
+// the chunk's rows to shared memory, every thread finds the row of its first interval there (binary search) and walks 16
+// consecutive intervals. Rows that hold a malformed interval are flagged and listed: the closed form of the sorting
+// kernels is only equal to the reference's heap sweep for well-formed rows, so those rows are computed by literal_kernel
+// (the reference accepts such input and gives a deterministic answer, stack.rs:61-139).
+constexpr uint32_t kValidateThreads = 256, kValidatePer = kValidateChunk / kValidateThreads, kValidateRows = 1024;
 
-__global__ void __launch_bounds__(256) validate_kernel(const uint2 *__restrict__ iv, const uint32_t *__restrict__ rowptr,
-                                                       const uint32_t *__restrict__ len, uint32_t n_reads, uint32_t n_iv, DevRowStats *out,
-                                                       uint32_t *lit_list, uint32_t *lit_count, uint32_t *bad_row_bits) {
-    const uint32_t lane = lane_id(), warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t n_chunks = (n_iv + kValidateChunk - 1u) / kValidateChunk;
-    const uint4 *iv4 = reinterpret_cast<const uint4 *>(iv);  // two intervals per load (chunks start at even intervals)
+__global__ void __launch_bounds__(kValidateThreads) validate_kernel(const uint2 *__restrict__ iv, const uint32_t *__restrict__ rowptr,
+                                                                    const uint32_t *__restrict__ len, uint32_t n_reads, uint32_t n_iv,
+                                                                    const uint32_t *__restrict__ chunk_row, DevRowStats *out, uint32_t *lit_list,
+                                                                    uint32_t *lit_count, uint32_t *bad_row_bits) {
+    // the chunk's intervals (coalesced loads; one pad slot per thread's stretch keeps the later reads conflict-free) and
+    // the row pointers / lengths of its first kValidateRows rows (a chunk with more rows - empty or tiny ones - finishes
+    // on the row pointers in memory)
+    __shared__ uint2 iv_s[kValidateChunk + kValidateThreads];
+    __shared__ uint32_t rp_s[kValidateRows + 2], ln_s[kValidateRows + 1], s_bad[2];
+    const uint32_t tid = threadIdx.x, n_chunks = (n_iv + kValidateChunk - 1u) / kValidateChunk;
+    if (tid < 2u) s_bad[tid] = 0u;
     uint32_t bad = 0, bad_rows = 0;
-    for (uint32_t ch = warp; ch < n_chunks; ch += n_warps) {
+    for (uint32_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
         const uint32_t P0 = ch * kValidateChunk, P1 = min(P0 + kValidateChunk, n_iv);
-        uint32_t r0;  // the row interval P0 lies in: the last row whose first interval is at or before P0
-        {
-            uint32_t lo = 0, hi = n_reads;  // rowptr[lo] <= P0 < rowptr[hi]
+        const uint32_t w0 = __ldg(chunk_row + ch), r_last = ch + 1u < n_chunks ? __ldg(chunk_row + ch + 1u) : n_reads - 1u;
+        const uint32_t n_rows = min(r_last - w0 + 1u, kValidateRows + 1u);  // rows of the chunk that the window holds
+        __syncthreads();
+#pragma unroll
+        for (uint32_t u = 0; u < kValidatePer; ++u) {
+            const uint32_t x = tid + u * kValidateThreads;  // local interval
+            if (P0 + x < P1) iv_s[x + (x / kValidatePer)] = __ldg(iv + P0 + x);
+        }
+        for (uint32_t t = tid; t <= n_rows; t += kValidateThreads) {
+            rp_s[t] = __ldg(rowptr + min(w0 + t, n_reads));
+            if (t < n_rows) ln_s[t] = __ldg(len + min(w0 + t, n_reads - 1u));
+        }
+        __syncthreads();
+        const uint32_t i0 = P0 + tid * kValidatePer;
+        if (i0 >= P1) continue;
+        // local row of interval i0: the last row of the window that starts at or before i0
+        uint32_t j;
+        if (rp_s[n_rows] <= i0) {  // behind the window: look the row up in memory
+            uint32_t glo = w0 + n_rows, ghi = n_reads;
+            while (ghi - glo > 1u) {
+                const uint32_t mid = (glo + ghi) >> 1;
+                if (__ldg(rowptr + mid) <= i0) glo = mid;
+                else ghi = mid;
+            }
+            j = glo - w0;
+        } else {
+            uint32_t lo = 0, hi = n_rows;  // rp_s[lo] <= i0 < rp_s[hi]
             while (hi - lo > 1u) {
                 const uint32_t mid = (lo + hi) >> 1;
-                if (__ldg(rowptr + mid) <= P0) lo = mid;
+                if (rp_s[mid] <= i0) lo = mid;
                 else hi = mid;
             }
-            r0 = lo;
+            j = lo;
         }
-        // window of 32 rows from r0: lane j holds the end and the length of row r0 + j
-        uint32_t p1 = __ldg(rowptr + min(r0 + lane, n_reads - 1u) + 1u), l = __ldg(len + min(r0 + lane, n_reads - 1u));
-        // (the window behind it is already on its way: moving on must not wait for memory)
-        uint32_t p1n = __ldg(rowptr + min(r0 + 32u + lane, n_reads - 1u) + 1u), ln = __ldg(len + min(r0 + 32u + lane, n_reads - 1u));
-        uint32_t rr = 0;  // first row of the window that ends behind the last step
-        const uint4 none = make_uint4(0u, 1u, 0u, 1u);
-        auto load2 = [&](uint32_t i) {  // intervals i, i + 1 (i even); beyond the buffer's last interval: a well-formed dummy
-            if (i + 1u < n_iv) return __ldg(iv4 + (i >> 1));
-            uint4 x = none;
-            if (i < n_iv) {
-                const uint2 y = __ldg(iv + i);
-                x.x = y.x, x.y = y.y;
+        const uint2 *mine = iv_s + tid * (kValidatePer + 1u);
+#pragma unroll
+        for (uint32_t u = 0; u < kValidatePer; ++u) {
+            const uint32_t i = i0 + u;
+            if (i >= P1) break;
+            const uint2 v = mine[u];
+            while (j < n_rows && rp_s[j + 1u] <= i) ++j;  // (skips empty rows)
+            uint32_t row = w0 + j, lj;
+            if (j >= n_rows) {  // off the window: row pointers in memory
+                while (__ldg(rowptr + row + 1u) <= i) ++row;
+                j = row - w0;
+                lj = __ldg(len + row);
+            } else {
+                lj = ln_s[j];
             }
-            return x;
-        };
-        uint4 va = P0 + 2u * lane < P1 ? load2(P0 + 2u * lane) : none, vb = P0 + 64u + 2u * lane < P1 ? load2(P0 + 64u + 2u * lane) : none;
-        for (uint32_t base = P0; base < P1; base += 64u) {
-            const uint32_t i0 = base + 2u * lane;
-            const uint4 vc = va;
-            va = vb;
-            vb = i0 + 128u < P1 ? load2(i0 + 128u) : none;
-            uint32_t l0 = 0, l1 = 0, row0 = 0, row1 = 0;
-            bool f0 = false, f1 = false;
-            for (;;) {  // rows that end inside this step (uniform loop; the window moves on when it is used up)
-                if (rr == 32u) {
-                    r0 += 32u;
-                    p1 = p1n;
-                    l = ln;
-                    p1n = __ldg(rowptr + min(r0 + 32u + lane, n_reads - 1u) + 1u);
-                    ln = __ldg(len + min(r0 + 32u + lane, n_reads - 1u));
-                    rr = 0u;
+            if (!(v.x < v.y && v.y <= lj)) {
+                ++bad;
+                const uint32_t bit = 1u << (row & 31u);
+                if (!(atomicOr(bad_row_bits + (row >> 5), bit) & bit)) {
+                    lit_list[atomicAdd(lit_count, 1u)] = row;
+                    ++bad_rows;
                 }
-                const uint32_t e = __shfl_sync(FULL, p1, rr), le = __shfl_sync(FULL, l, rr);
-                if (!f0 && i0 < e) f0 = true, l0 = le, row0 = r0 + rr;
-                if (!f1 && i0 + 1u < e) f1 = true, l1 = le, row1 = r0 + rr;
-                if (e > base + 63u || r0 + rr + 1u >= n_reads) break;  // this row goes on behind the step (or is the last one)
-                ++rr;
             }
-            auto check = [&](uint32_t i, uint32_t b, uint32_t e, uint32_t lj, uint32_t row) {
-                if (i < P1 && !(b < e && e <= lj)) {
-                    ++bad;
-                    const uint32_t bit = 1u << (row & 31u);
-                    if (!(atomicOr(bad_row_bits + (row >> 5), bit) & bit)) {
-                        lit_list[atomicAdd(lit_count, 1u)] = row;
-                        ++bad_rows;
-                    }
-                }
-            };
-            check(i0, vc.x, vc.y, l0, row0);
-            check(i0 + 1u, vc.z, vc.w, l1, row1);
         }
     }
-    bad = warp_sum(bad);
-    bad_rows = warp_sum(bad_rows);
-    if (lane == 0 && bad) {
-        atomicAdd(&out->malformed, bad);
-        atomicAdd(&out->malformed_rows, bad_rows);
+    if (bad) atomicAdd(&s_bad[0], bad);
+    if (bad_rows) atomicAdd(&s_bad[1], bad_rows);
+    __syncthreads();
+    if (tid == 0 && s_bad[0]) {
+        atomicAdd(&out->malformed, s_bad[0]);
+        atomicAdd(&out->malformed_rows, s_bad[1]);
     }
 }
 
@@ -1309,7 +1345,8 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, size_t *tota
     const uint64_t cap = (uint64_t)a.n_iv + a.n_reads + ((uint64_t)a.n_iv + a.n_reads) / 2 + 2ull * a.n_reads + 4096ull * kStageChunk;  // + one open chunk per resident warp
     w.stage_cap = cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cap;
     w.stage = reinterpret_cast<uint2 *>(take(sizeof(uint2) * ((size_t)w.stage_cap + 1)));
-    w.part_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * ((size_t)w.n_parts + 8)));
+    w.part_total = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)w.n_parts + 8)));
+    w.part_prefix = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)w.n_parts + 8)));
     w.big_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.scan_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.huge_keys = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (huge_keys + 1)));
@@ -1381,10 +1418,12 @@ const DevCfg *dev_cfg() {
 
 }  // namespace
 
-int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream) {
+size_t chunk_table_words(uint32_t n_iv) { return (size_t)n_iv / kValidateChunk + 2; }
+
+int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, uint32_t *chunk_row, cudaStream_t stream) {
     if (cudaMemsetAsync(out, 0, sizeof(DevRowStats), stream) != cudaSuccess) return -1;
     if (n_reads == 0) return 0;
-    row_stats_kernel<<<(n_reads + 1023u) / 1024u, 1024, 0, stream>>>(rowptr, len, n_reads, out);
+    row_stats_kernel<<<(n_reads + 1023u) / 1024u, 1024, 0, stream>>>(rowptr, len, n_reads, out, chunk_row);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -1397,12 +1436,13 @@ int launch_upload_kernels(const DetectArgs &a, DevRowStats *out, cudaStream_t st
     size_t total = 0;
     Work w = carve(a, a.rows.huge_keys, a.rows.n_big, &total);
     if (total > a.scratch_bytes) return -1;
-    uint32_t grid = (uint32_t)dc->n_sm * 8u;
-    const uint32_t want = ((a.n_iv + kValidateChunk - 1u) / kValidateChunk + 7u) / 8u;  // one chunk per warp, 8 warps per CTA
-    if (grid > want) grid = std::max(want, 1u);
-    if (cudaMemsetAsync(w.part_desc, 0, sizeof(unsigned long long) * (size_t)w.n_parts, stream) != cudaSuccess) return -1;
     if (cudaMemsetAsync(w.bad_rows, 0, sizeof(uint32_t) * ((size_t)a.n_reads / 32 + 1), stream) != cudaSuccess) return -1;
-    if (a.n_iv) validate_kernel<<<grid, 256, 0, stream>>>(a.iv, a.rowptr, a.len, a.n_reads, a.n_iv, out, w.lit_list, a.counters + kCntLiteralList, w.bad_rows);
+    if (a.n_iv) {
+        const uint32_t n_chunks = (a.n_iv + kValidateChunk - 1u) / kValidateChunk;
+        const uint32_t grid = std::min(n_chunks, (uint32_t)dc->n_sm * 6u);
+        validate_kernel<<<grid, kValidateThreads, 0, stream>>>(a.iv, a.rowptr, a.len, a.n_reads, a.n_iv, a.chunk_row, out, w.lit_list,
+                                                               a.counters + kCntLiteralList, w.bad_rows);
+    }
     scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, make_plan(a));
     return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
@@ -1473,7 +1513,9 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         literal_kernel<<<grid, 64, 0, stream>>>(a, w, coverage, a.n_literal);
         ++launches;
     }
+    totals_kernel<<<(w.n_parts + 7u) / 8u, 256, 0, stream>>>(a, w);
     order_kernel<<<w.n_parts, kOrderThreads, 0, stream>>>(a, w, not_coverage);
+    ++launches;
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;

@@ -141,6 +141,7 @@ struct yb_ctx {
     DeviceBuf<uint2> d_iv, d_gaps;
     DeviceBuf<uint8_t> d_cls, d_bitmap, d_scratch;
     DeviceBuf<yb::DevRowStats> d_rowstats;
+    DeviceBuf<uint32_t> d_chunk_row;
     PinnedBuf<yb::DevRowStats> h_rowstats;
     PinnedBuf<uint32_t> h_peer_step;
     uint8_t *ext_bitmap = nullptr;  // yb_bind_device_bitmap
@@ -417,6 +418,7 @@ void yb_destroy(yb_ctx *c) {
     c->d_bitmap.release();
     c->d_scratch.release();
     c->d_rowstats.release();
+    c->d_chunk_row.release();
     c->h_rowstats.release();
     delete c;
 }
@@ -767,6 +769,7 @@ static int detect_args(yb_ctx *c, yb::DetectArgs *out) {
     a.gaps = c->d_gaps.p;
     a.bitmap = c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p;
     a.counters = c->d_counters.p;
+    a.chunk_row = c->d_chunk_row.p;
     a.side_stream = c->side_stream;
     a.ev_fork = c->ev_fork;
     a.ev_join = c->ev_join;
@@ -803,14 +806,15 @@ int yb_upload(yb_ctx *c) {
     if (!c->d_rowptr.reserve(n + 1) || !c->d_len.reserve(n + 1) || !c->d_iv.reserve(m + 2))
         return c->fail(YB_ERR_NOMEM, "device allocation failed (%zu reads, %zu intervals)", n, m);
     if (int rc = ensure_result_buffers(c)) return rc;
-    if (!c->d_rowstats.reserve(1) || !c->h_rowstats.reserve(1)) return c->fail(YB_ERR_NOMEM, "allocation failed");
+    if (!c->d_rowstats.reserve(1) || !c->h_rowstats.reserve(1) || !c->d_chunk_row.reserve(yb::chunk_table_words(c->n_iv)))
+        return c->fail(YB_ERR_NOMEM, "allocation failed");
     if (n) {
         YB_CUDA(c, cudaMemcpyAsync(c->d_rowptr.p, c->rowptr_host(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, c->stream));
         YB_CUDA(c, cudaMemcpyAsync(c->d_len.p, c->len_host(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
     }
     // size classes, big-row scratch needs and input sanity come from one small kernel over rowptr / len; its
     // 128-byte result crosses PCIe while the interval buffer is still on its way
-    const int sl = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->stream);
+    const int sl = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->d_chunk_row.p, c->stream);
     if (sl < 0) return c->cuda_fail(cudaGetLastError(), "row statistics kernel");
     c->stats.kernel_launches += (uint64_t)sl;
     YB_CUDA(c, cudaMemcpyAsync(c->h_rowstats.p, c->d_rowstats.p, sizeof(yb::DevRowStats), cudaMemcpyDeviceToHost, c->stream));
@@ -851,6 +855,7 @@ int yb_upload(yb_ctx *c) {
         a.max_k = c->max_k;
         a.rows = c->rows;
         a.counters = c->d_counters.p;
+        a.chunk_row = c->d_chunk_row.p;
         a.scratch = c->d_scratch.p;
         a.scratch_bytes = c->d_scratch.cap;
         const int ul = yb::launch_upload_kernels(a, c->d_rowstats.p, c->stream);
@@ -930,7 +935,7 @@ int yb_time_upload_kernels(yb_ctx *c, float *ms_out) {
     int rc = detect_args(c, &a);
     if (rc == YB_OK) {
         cudaEventRecord(e0, c->stream);
-        const int l0 = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->stream);
+        const int l0 = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->d_chunk_row.p, c->stream);
         const int l1 = yb::launch_upload_kernels(a, c->d_rowstats.p, c->stream);
         cudaEventRecord(e1, c->stream);
         if (l0 < 0 || l1 < 0 || cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(ms_out, e0, e1) != cudaSuccess)
@@ -1005,6 +1010,7 @@ int yb_download(yb_ctx *c) {
     if (set[yb::kCntPeerTimeout] || hc[yb::kCntPeerTimeoutWait])
         return c->fail(YB_ERR_STATE, "peer all-gather: a rank never signalled its step (%u / %u)", set[yb::kCntPeerTimeout],
                        hc[yb::kCntPeerTimeoutWait]);
+    if (hc[yb::kCntOrderTimeout]) return c->fail(YB_ERR_STATE, "internal error: the ordering kernel did not complete");
     if (set[yb::kCntStageOverflow])
         return c->fail(YB_ERR_STATE, "internal error: bad-region staging buffer overflow (%u reads)", set[yb::kCntStageOverflow]);
     c->n_gaps = c->h_gap_ptr.p[n];

@@ -23,7 +23,7 @@ enum Counter : uint32_t {
     kCntTileWide = 5,    // the same for the long reads' kernel
     kCntHugeBump = 6,    // bump allocator (in u32 keys) of the global-scratch tier
     kCntStage = 11,      // bump allocator (in pairs) of the bad-region staging buffer
-    kCntTicket = 13,     // order_kernel: dynamic part index (decoupled look-back needs in-order starts)
+    kCntTotalsDone = 13, // totals_kernel: CTAs finished (the last one scans the part totals)
     kCntStageOverflow = 14,  // rows whose bad regions did not fit the staging buffer (must stay 0)
     kCntPeerTimeout = 15,  // a peer never signalled the previous step (a rank died or never launched)
     kCntDone = 16,       // order_kernel: parts finished (the last one closes the step)
@@ -37,6 +37,7 @@ constexpr uint32_t kCntEpoch = 2 * kNumCounters;          // number of detect st
 constexpr uint32_t kCntBigList = 2 * kNumCounters + 1;    // upload: rows with more than 512 intervals (big tier)
 constexpr uint32_t kCntLiteralList = 2 * kNumCounters + 2;  // upload: rows with a malformed interval
 constexpr uint32_t kCntScanList = 2 * kNumCounters + 4;     // upload: big rows of the position-scan path
+constexpr uint32_t kCntOrderTimeout = 2 * kNumCounters + 5; // order_kernel: the closing CTA gave up waiting for the others
 constexpr uint32_t kCntPeerTimeoutWait = 2 * kNumCounters + 3;  // peer_wait_kernel gave up (a rank died or never launched)
 constexpr uint32_t kCntClassCursor = 2 * kNumCounters + 8;  // upload: kNumClasses cursors of the worklist scatter
 constexpr uint32_t kCounterWords = 2 * kNumCounters + 8 + 24;
@@ -124,7 +125,8 @@ struct DetectArgs {
     uint8_t *peer_slot[16];  // peer p's gather buffer + rank * slot_bytes (the slot of even steps)
     size_t peer_parity_bytes; // n_ranks * slot_bytes: odd steps use the second half of every gather buffer
     uint32_t *peer_flag[16]; // peer p's flag array (word q: steps rank q has finished; word 31: steps this rank has finished)
-    uint32_t *counters;      // kNumCounters
+    uint32_t *counters;      // kCounterWords
+    const uint32_t *chunk_row;  // launch_row_stats: the row every chunk of validate_kernel starts in
     // host side only: a second stream and two events so that the CTA tier (rows with k > 512) runs beside the register
     // tier instead of in front of it (null: same stream, one after the other)
     cudaStream_t side_stream;
@@ -149,7 +151,9 @@ struct DevRowStats {
     uint32_t pad2_[2];
 };
 // Zeroes *out and fills it from the device-resident rowptr / len (one kernel on `stream`). Returns launches or -1.
-int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream);
+// chunk_row (chunk_table_words(n_iv) words): the row every chunk of validate_kernel starts in.
+size_t chunk_table_words(uint32_t n_iv);
+int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, uint32_t *chunk_row, cudaStream_t stream);
 
 // Once per uploaded CSR, behind the interval copy (the CSR cannot change afterwards; both depend on rowptr / len / the
 // intervals only, not on the threshold — the reference builds its read index, a hash map, while it ingests):
