@@ -83,7 +83,6 @@ constexpr uint32_t kSortThreads = kSortWarps * 32;
 #endif
 constexpr uint32_t kBufIntervals = YB_BUF_INTERVALS;  // row slots of a warp's slab buffer: a batch of class G holds min(floor(32 / G),
                                                       // floor(kBufIntervals / (kE G + 2))) rows; 32 (kE + 2) = 32 rows of the G = 1 class
-constexpr uint32_t kValidateChunk = 4096;      // intervals per CTA of validate_kernel
 constexpr uint32_t kScatterRows = 1024;        // rows per CTA of scatter_kernel
 #ifndef YB_ORDER_THREADS
 #define YB_ORDER_THREADS 256
@@ -116,8 +115,7 @@ struct Work {
     uint32_t *part_total;            // n_parts: bad regions of every part of kPartRows rows (totals_kernel)
     uint32_t *part_prefix;           // their exclusive prefix (the last CTA of totals_kernel)
     uint32_t n_parts;
-    uint32_t *lit_list;              // rows holding a malformed interval (they take the literal heap sweep)
-    uint32_t *bad_rows;              // one bit per row: the row holds a malformed interval (validate_kernel)
+    uint32_t *lit_list;              // rows holding a malformed interval, found by a validating step (they take the literal heap sweep)
     uint32_t *big_list;              // rows with k > kSmallMaxK that are sorted by a CTA
     uint32_t *scan_list;             // rows with k > kSmallMaxK that are scanned by position (big_row_scans)
     uint32_t *huge_keys;             // event keys of rows beyond the shared-memory tier
@@ -132,16 +130,13 @@ __global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Wor
     if (tid < (uint32_t)kNumClasses) s_cnt[tid] = 0u;
     __syncthreads();
     int cls = -2;  // 0 .. kNumClasses-1: lane-group classes; -1: big row
-    uint32_t p0 = 0, k = 0, len = 0, lit = 0;
+    uint32_t p0 = 0, k = 0, len = 0;
     if (r < a.n_reads) {
         p0 = __ldg(a.rowptr + r);
         k = __ldg(a.rowptr + r + 1) - p0;
         len = __ldg(a.len + r);
         cls = class_of_row(k, len);
-        // a row with a malformed interval keeps its place in its class (the host sized the classes before the intervals
-        // were looked at) but its record is not valid: the sorting kernels skip it, literal_kernel computes it
-        lit = (__ldg(w.bad_rows + (r >> 5)) >> (r & 31u)) & 1u;
-        if (cls < 0 && !lit) {
+        if (cls < 0) {
             if (big_row_scans(k, len)) w.scan_list[atomicAdd(a.counters + kCntScanList, 1u)] = r;
             else w.big_list[atomicAdd(a.counters + kCntBigList, 1u)] = r;
         }
@@ -154,7 +149,7 @@ __global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Wor
     __syncthreads();
     if (tid < (uint32_t)kNumClasses && s_cnt[tid]) s_base[tid] = atomicAdd(a.counters + kCntClassCursor + tid, s_cnt[tid]);
     __syncthreads();
-    if (cls >= 0) w.recs[tab.entry_base[cls] + s_base[cls] + wbase + rank] = make_uint4(r, p0, k | ((uint32_t)cls << 16) | (lit ? 0u : kRecValid), len);
+    if (cls >= 0) w.recs[tab.entry_base[cls] + s_base[cls] + wbase + rank] = make_uint4(r, p0, k | ((uint32_t)cls << 16) | kRecValid, len);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -370,7 +365,7 @@ __device__ void cta_row(const DetectArgs &a, const Work &w, uint32_t *cnt, uint3
             for (int t = 0; t < E; ++t) eb[t] = Kx[t];
         }
     }
-    if (__any_sync(FULL, bad_iv) && lane == 0) atomicAdd(cnt + kCntMalformed, 1u);
+    if (a.validate && bad_iv) sh[12] = 1u;  // (cleared by thread 0 at the end of the row)
     __syncthreads();
     cta_merge_levels<PK>(keys, K, PK ? 1u : 2u);
     // ---- crossings: thread t owns the contiguous slots [i0, i1) ----
@@ -441,7 +436,13 @@ __device__ void cta_row(const DetectArgs &a, const Work &w, uint32_t *cnt, uint3
         } else {
             atomicAdd(cnt + kCntStageOverflow, 1u);
         }
-        w.meta[r] = make_uint2(at, ng);
+        if (sh[12]) {  // validating step, malformed interval: literal_kernel computes the row (see process_batch_t)
+            w.lit_list[atomicAdd(a.counters + kCntLiteralList, 1u)] = r;
+            atomicAdd(a.counters + kCntMalformedIv, 1u);  // (at least one; the exact count is not kept on this path)
+            sh[12] = 0u;
+        } else {
+            w.meta[r] = make_uint2(at, ng);
+        }
     }
     __syncthreads();
 }
@@ -449,6 +450,8 @@ __device__ void cta_row(const DetectArgs &a, const Work &w, uint32_t *cnt, uint3
 __global__ void __launch_bounds__(kCtaThreads) big_kernel(DetectArgs a, Work w, uint32_t c, uint32_t smem_words) {
     extern __shared__ __align__(16) uint32_t cta_smem[];
     __shared__ uint32_t sh[16];
+    if (threadIdx.x == 0) sh[12] = 0u;
+    __syncthreads();
     const uint32_t n_big = min((uint32_t)(a.rows.n_big - a.rows.n_scan), __ldcg(a.counters + kCntBigList));  // (rows redone by literal_kernel are not listed)
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
@@ -535,12 +538,17 @@ __global__ void __launch_bounds__(kScanThreads, 2) bigscan_kernel(DetectArgs a, 
     for (uint32_t j = blockIdx.x; j < n_scan; j += gridDim.x) {
         const uint32_t r = r_n, s = s_n, k = k_n, len = len_n;
         const uint32_t n_pos = len + 1u;  // positions 0 .. len
-        if (tid == 0) s_v[2] = atomicAdd(cnt + kCntStage, k + 1u);  // the pair list P[q] = (D_{q-1}, U_q), q = 0 .. n_up <= k
+        if (tid == 0) {
+            s_v[2] = atomicAdd(cnt + kCntStage, k + 1u);  // the pair list P[q] = (D_{q-1}, U_q), q = 0 .. n_up <= k
+            s_v[3] = 0u;                                  // validating step: the row holds a malformed interval
+        }
+        uint32_t nbad = 0;
         uint32_t depth = 0, ups = 0, downs = 0;  // carried from window to window (the same in every thread)
         for (uint32_t lo = 0; lo < n_pos; lo += kScanWindow) {
             const uint32_t m = min(kScanWindow, n_pos - lo);
             __syncthreads();  // the previous window is cleared
             auto count = [&](const uint2 v) {
+                if (a.validate && lo == 0u) nbad += !(v.x < v.y && v.y <= len);
                 const uint32_t xb = v.x - lo, xe = v.y - lo;
                 if (xb < m) {
                     atomicAdd(&cnt_x[xb], 1u);
@@ -555,6 +563,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) bigscan_kernel(DetectArgs a, 
             for (uint32_t u = 0; u < NPF; ++u)
                 if (tid + u * kScanThreads < k) count(pf[u]);
             for (uint32_t i = tid + NPF * kScanThreads; i < k; i += kScanThreads) count(__ldg(a.iv + s + i));
+            if (nbad) s_v[3] = 1u;
             if (lo + kScanWindow >= n_pos) {  // last window: the registers are free for the next row
                 fetch_meta(j + gridDim.x);
             }
@@ -606,10 +615,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) bigscan_kernel(DetectArgs a, 
             ups += tot_ud & 0xFFFFu;
             downs += tot_ud >> 16;
         }
+        if (nbad) atomicAdd(a.counters + kCntMalformedIv, nbad);
         __syncthreads();
         if (tid == 0) {
             const uint32_t base = s_v[2], n_up = ups, U0 = s_v[0], Dl = s_v[1];
-            if ((uint64_t)base + k + 1u <= w.stage_cap) {
+            if (s_v[3]) {  // not this kernel's business (see process_batch_t): literal_kernel computes the row
+                w.lit_list[atomicAdd(a.counters + kCntLiteralList, 1u)] = r;
+            } else if ((uint64_t)base + k + 1u <= w.stage_cap) {
                 uint32_t *P = reinterpret_cast<uint32_t *>(w.stage + base);
                 P[0] = 0u;
                 P[2u * n_up + 1u] = len;
@@ -719,6 +731,7 @@ __device__ __forceinline__ void issue_batch(const DetectArgs &a, const ClassTab 
 // inside a CTA from a shared-memory counter: a global counter would cost every warp an L2 round trip per batch, because
 // ptxas turns any atomic in a divergent region into a warp-aggregated one whose result is broadcast by a shuffle on the
 // spot (no way to keep it in flight behind a batch).
+template <bool VAL>
 __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Work w, ClassTab tab, uint32_t c, PipeMul pm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_next;
@@ -776,8 +789,8 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
             if (item1 < n_items) issue_batch(a, tab, buf, &ws.mbar, ws.rec[s][lane], cls1, lane);
         };
 #define YB_CASE(gi)                                                                                                        \
-    case gi: process_batch_t<class_lanes_c(gi), true>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;             \
-    case gi + kNumG: process_batch_t<class_lanes_c(gi), false>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
+    case gi: process_batch_t<class_lanes_c(gi), true, VAL>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;        \
+    case gi + kNumG: process_batch_t<class_lanes_c(gi), false, VAL>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;
         switch (cls0) {  // classes 0 .. kNumG-1: packed rows, G = class_lanes(class); kNumG .. : the same sizes for long reads
             YB_CASE(0) YB_CASE(1) YB_CASE(2) YB_CASE(3) YB_CASE(4) YB_CASE(5) YB_CASE(6)
 #if YB_KE == 16
@@ -1017,7 +1030,15 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
     for (uint32_t i = tid; i < kNumCounters; i += kOrderThreads) other[i] = 0u;
     __threadfence();
     __syncthreads();
-    if (tid == 0) a.counters[kCntEpoch] = ep + 1u;
+    if (tid == 0) {
+        a.counters[kCntEpoch] = ep + 1u;
+        if (a.validate) {  // what this step's validation found, for the host; the running counts start over
+            a.counters[kCntLiteralLast] = a.counters[kCntLiteralList];
+            a.counters[kCntMalformedLast] = a.counters[kCntMalformedIv];
+            a.counters[kCntLiteralList] = 0u;
+            a.counters[kCntMalformedIv] = 0u;
+        }
+    }
     if (a.n_peers) {
         __threadfence_system();  // every part's peer stores (fenced by their writers before kCntDone) before the flags
         if (tid < a.n_peers) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flag[tid] + a.rank), "r"(peer_step + 1u) : "memory");
@@ -1070,7 +1091,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint32_t *__restric
 // row_stats_kernel (upload time): size-class histogram, big-row scratch needs, input sanity
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ len,
-                                                          uint32_t n_reads, DevRowStats *out, uint32_t *chunk_row) {
+                                                          uint32_t n_reads, DevRowStats *out) {
     __shared__ uint32_t s_cnt[kNumClasses + 1], s_max, s_bad[3];
     (void)0;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, r = blockIdx.x * 1024u + tid;
@@ -1086,8 +1107,6 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
             atomicAdd(&s_bad[0], 1u);
         } else {
             k = p1 - p0;
-            // validate_kernel cuts the interval buffer into chunks of kValidateChunk: the row a chunk starts in
-            for (uint32_t ch = (p0 + kValidateChunk - 1u) / kValidateChunk; k && (uint64_t)ch * kValidateChunk < p1; ++ch) chunk_row[ch] = r;
             cls = class_of_row(k, l);
             if (cls < 0) {  // big row: rare, straight to the global sums
                 cls = kNumClasses;
@@ -1119,97 +1138,6 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
         if (s_bad[0]) atomicAdd(&out->bad_rowptr, s_bad[0]);
         if (s_bad[1]) atomicAdd(&out->bad_len, s_bad[1]);
         if (s_bad[2]) atomicAdd(&out->n_wide, s_bad[2]);
-    }
-}
-
-// validate_kernel (upload time): 0 <= begin < end <= length for every interval. The interval buffer is cut into chunks
-// of kValidateChunk intervals whatever the rows look like (a read with 5000 intervals is not one thread's problem). A CTA
-// takes a chunk: row_stats_kernel left the row every chunk starts in, so the CTA copies the row pointers and lengths of
-// the chunk's rows to shared memory, every thread finds the row of its first interval there (binary search) and walks 16
-// consecutive intervals. Rows that hold a malformed interval are flagged and listed: the closed form of the sorting
-// kernels is only equal to the reference's heap sweep for well-formed rows, so those rows are computed by literal_kernel
-// (the reference accepts such input and gives a deterministic answer, stack.rs:61-139).
-constexpr uint32_t kValidateThreads = 256, kValidatePer = kValidateChunk / kValidateThreads, kValidateRows = 1024;
-
-__global__ void __launch_bounds__(kValidateThreads) validate_kernel(const uint2 *__restrict__ iv, const uint32_t *__restrict__ rowptr,
-                                                                    const uint32_t *__restrict__ len, uint32_t n_reads, uint32_t n_iv,
-                                                                    const uint32_t *__restrict__ chunk_row, DevRowStats *out, uint32_t *lit_list,
-                                                                    uint32_t *lit_count, uint32_t *bad_row_bits) {
-    // the chunk's intervals (coalesced loads; one pad slot per thread's stretch keeps the later reads conflict-free) and
-    // the row pointers / lengths of its first kValidateRows rows (a chunk with more rows - empty or tiny ones - finishes
-    // on the row pointers in memory)
-    __shared__ uint2 iv_s[kValidateChunk + kValidateThreads];
-    __shared__ uint32_t rp_s[kValidateRows + 2], ln_s[kValidateRows + 1], s_bad[2];
-    const uint32_t tid = threadIdx.x, n_chunks = (n_iv + kValidateChunk - 1u) / kValidateChunk;
-    if (tid < 2u) s_bad[tid] = 0u;
-    uint32_t bad = 0, bad_rows = 0;
-    for (uint32_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
-        const uint32_t P0 = ch * kValidateChunk, P1 = min(P0 + kValidateChunk, n_iv);
-        const uint32_t w0 = __ldg(chunk_row + ch), r_last = ch + 1u < n_chunks ? __ldg(chunk_row + ch + 1u) : n_reads - 1u;
-        const uint32_t n_rows = min(r_last - w0 + 1u, kValidateRows + 1u);  // rows of the chunk that the window holds
-        __syncthreads();
-#pragma unroll
-        for (uint32_t u = 0; u < kValidatePer; ++u) {
-            const uint32_t x = tid + u * kValidateThreads;  // local interval
-            if (P0 + x < P1) iv_s[x + (x / kValidatePer)] = __ldg(iv + P0 + x);
-        }
-        for (uint32_t t = tid; t <= n_rows; t += kValidateThreads) {
-            rp_s[t] = __ldg(rowptr + min(w0 + t, n_reads));
-            if (t < n_rows) ln_s[t] = __ldg(len + min(w0 + t, n_reads - 1u));
-        }
-        __syncthreads();
-        const uint32_t i0 = P0 + tid * kValidatePer;
-        if (i0 >= P1) continue;
-        // local row of interval i0: the last row of the window that starts at or before i0
-        uint32_t j;
-        if (rp_s[n_rows] <= i0) {  // behind the window: look the row up in memory
-            uint32_t glo = w0 + n_rows, ghi = n_reads;
-            while (ghi - glo > 1u) {
-                const uint32_t mid = (glo + ghi) >> 1;
-                if (__ldg(rowptr + mid) <= i0) glo = mid;
-                else ghi = mid;
-            }
-            j = glo - w0;
-        } else {
-            uint32_t lo = 0, hi = n_rows;  // rp_s[lo] <= i0 < rp_s[hi]
-            while (hi - lo > 1u) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (rp_s[mid] <= i0) lo = mid;
-                else hi = mid;
-            }
-            j = lo;
-        }
-        const uint2 *mine = iv_s + tid * (kValidatePer + 1u);
-#pragma unroll
-        for (uint32_t u = 0; u < kValidatePer; ++u) {
-            const uint32_t i = i0 + u;
-            if (i >= P1) break;
-            const uint2 v = mine[u];
-            while (j < n_rows && rp_s[j + 1u] <= i) ++j;  // (skips empty rows)
-            uint32_t row = w0 + j, lj;
-            if (j >= n_rows) {  // off the window: row pointers in memory
-                while (__ldg(rowptr + row + 1u) <= i) ++row;
-                j = row - w0;
-                lj = __ldg(len + row);
-            } else {
-                lj = ln_s[j];
-            }
-            if (!(v.x < v.y && v.y <= lj)) {
-                ++bad;
-                const uint32_t bit = 1u << (row & 31u);
-                if (!(atomicOr(bad_row_bits + (row >> 5), bit) & bit)) {
-                    lit_list[atomicAdd(lit_count, 1u)] = row;
-                    ++bad_rows;
-                }
-            }
-        }
-    }
-    if (bad) atomicAdd(&s_bad[0], bad);
-    if (bad_rows) atomicAdd(&s_bad[1], bad_rows);
-    __syncthreads();
-    if (tid == 0 && s_bad[0]) {
-        atomicAdd(&out->malformed, s_bad[0]);
-        atomicAdd(&out->malformed_rows, s_bad[1]);
     }
 }
 
@@ -1264,7 +1192,8 @@ __device__ __forceinline__ void lit_pop(uint32_t *h, uint32_t &n) {
     if (n) h[i] = x;
 }
 
-__global__ void __launch_bounds__(64) literal_kernel(DetectArgs a, Work w, uint32_t coverage, uint32_t n_lit) {
+__global__ void __launch_bounds__(64) literal_kernel(DetectArgs a, Work w, uint32_t coverage) {
+    const uint32_t n_lit = __ldcg(a.counters + kCntLiteralList);  // what the validating kernels of this step listed
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_lit; j += gridDim.x * blockDim.x) {
@@ -1351,7 +1280,6 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, size_t *tota
     w.scan_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.huge_keys = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (huge_keys + 1)));
     w.lit_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)a.n_reads + 1)));
-    w.bad_rows = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)a.n_reads / 32 + 2)));
     *total = off;
     return w;
 }
@@ -1403,8 +1331,9 @@ const DevCfg *dev_cfg() {
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return;
         if (cudaFuncSetAttribute(big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kCtaMaxSmemWords * sizeof(uint32_t))) != cudaSuccess) return;
         if (cudaFuncSetAttribute(bigscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes) != cudaSuccess) return;
-        if (cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_kernel, kSortThreads, kSortSmemBytes) != cudaSuccess || occ < 1) return;
+        if (cudaFuncSetAttribute(sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return;
+        if (cudaFuncSetAttribute(sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes) != cudaSuccess) return;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sort_kernel<true>, kSortThreads, kSortSmemBytes) != cudaSuccess || occ < 1) return;
         d.n_sm = sm;
         d.occ_sort = occ;
         d.ok = 1;
@@ -1418,16 +1347,14 @@ const DevCfg *dev_cfg() {
 
 }  // namespace
 
-size_t chunk_table_words(uint32_t n_iv) { return (size_t)n_iv / kValidateChunk + 2; }
-
-int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, uint32_t *chunk_row, cudaStream_t stream) {
+int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream) {
     if (cudaMemsetAsync(out, 0, sizeof(DevRowStats), stream) != cudaSuccess) return -1;
     if (n_reads == 0) return 0;
-    row_stats_kernel<<<(n_reads + 1023u) / 1024u, 1024, 0, stream>>>(rowptr, len, n_reads, out, chunk_row);
+    row_stats_kernel<<<(n_reads + 1023u) / 1024u, 1024, 0, stream>>>(rowptr, len, n_reads, out);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_upload_kernels(const DetectArgs &a, DevRowStats *out, cudaStream_t stream) {
+int launch_upload_kernels(const DetectArgs &a, cudaStream_t stream) {
     // a fresh CSR: both counter sets, the step number and the upload cursors start from zero
     if (cudaMemsetAsync(a.counters, 0, kCounterWords * sizeof(uint32_t), stream) != cudaSuccess) return -1;
     if (a.n_reads == 0) return 0;
@@ -1436,15 +1363,8 @@ int launch_upload_kernels(const DetectArgs &a, DevRowStats *out, cudaStream_t st
     size_t total = 0;
     Work w = carve(a, a.rows.huge_keys, a.rows.n_big, &total);
     if (total > a.scratch_bytes) return -1;
-    if (cudaMemsetAsync(w.bad_rows, 0, sizeof(uint32_t) * ((size_t)a.n_reads / 32 + 1), stream) != cudaSuccess) return -1;
-    if (a.n_iv) {
-        const uint32_t n_chunks = (a.n_iv + kValidateChunk - 1u) / kValidateChunk;
-        const uint32_t grid = std::min(n_chunks, (uint32_t)dc->n_sm * 6u);
-        validate_kernel<<<grid, kValidateThreads, 0, stream>>>(a.iv, a.rowptr, a.len, a.n_reads, a.n_iv, a.chunk_row, out, w.lit_list,
-                                                               a.counters + kCntLiteralList, w.bad_rows);
-    }
     scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, make_plan(a));
-    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 uint64_t huge_keys_for_row(uint64_t k) {
@@ -1503,14 +1423,14 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         if (items) {
             uint32_t grid = (uint32_t)dc->n_sm;
             if (grid > items) grid = items;
-            sort_kernel<<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage, pm);
+            if (a.validate) sort_kernel<true><<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage, pm);
+            else sort_kernel<false><<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage, pm);
             ++launches;
         }
     }
     if (forked && cudaStreamWaitEvent(stream, a.ev_join, 0) != cudaSuccess) return -1;
-    if (a.n_literal) {  // rows with a malformed interval: the reference's heap sweep itself, over what the kernels above skipped
-        const uint32_t grid = std::min((a.n_literal + 63u) / 64u, (uint32_t)dc->n_sm * 16u);
-        literal_kernel<<<grid, 64, 0, stream>>>(a, w, coverage, a.n_literal);
+    if (a.validate) {  // rows with a malformed interval: the reference's heap sweep itself, over what the kernels above listed
+        literal_kernel<<<(uint32_t)dc->n_sm, 64, 0, stream>>>(a, w, coverage);
         ++launches;
     }
     totals_kernel<<<(w.n_parts + 7u) / 8u, 256, 0, stream>>>(a, w);

@@ -114,7 +114,13 @@ struct yb_ctx {
     cudaEvent_t ev_upload = nullptr;   // last upload work on `stream` (a compute on another stream waits for it)
     cudaEvent_t ev_compute = nullptr;  // last detect step enqueued on a caller's stream (yb_download waits for it)
     bool compute_foreign = false;      // ev_compute is pending
-    bool literal_known = false;        // the upload's validation result (rows for the literal heap sweep) has been read
+    // The first detect step after an upload tests every interval it loads (0 <= begin < end <= length); rows that fail go
+    // to the literal heap sweep. Its two counts come back behind the step (4 + 4 bytes); if they are zero the next steps
+    // run the plain kernels.
+    bool validated = false;            // the counts of a validating step over this CSR are known
+    bool valid_pending = false;        // a validating step is in flight; ev_valid follows its counts' copy
+    cudaEvent_t ev_valid = nullptr;
+    PinnedBuf<uint32_t> h_valid;
     uint32_t n_literal = 0, n_malformed = 0;
     bool bulk_frozen = false;  // the CSR came straight from the parallel ingester: `pending` does not hold it
     std::string error;
@@ -141,7 +147,6 @@ struct yb_ctx {
     DeviceBuf<uint2> d_iv, d_gaps;
     DeviceBuf<uint8_t> d_cls, d_bitmap, d_scratch;
     DeviceBuf<yb::DevRowStats> d_rowstats;
-    DeviceBuf<uint32_t> d_chunk_row;
     PinnedBuf<yb::DevRowStats> h_rowstats;
     PinnedBuf<uint32_t> h_peer_step;
     uint8_t *ext_bitmap = nullptr;  // yb_bind_device_bitmap
@@ -323,6 +328,7 @@ static int open_device(yb_ctx *c) {
         c->side_stream = nullptr;
     }
     if (cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_valid, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming) != cudaSuccess) {
         e = cudaGetLastError();
         return c->fail(YB_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e));
@@ -398,6 +404,7 @@ void yb_destroy(yb_ctx *c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
+    if (c->ev_valid) cudaEventDestroy(c->ev_valid);
     if (c->ev_compute) cudaEventDestroy(c->ev_compute);
     c->h_peer_step.release();
     c->h_rowptr.release();
@@ -418,7 +425,7 @@ void yb_destroy(yb_ctx *c) {
     c->d_bitmap.release();
     c->d_scratch.release();
     c->d_rowstats.release();
-    c->d_chunk_row.release();
+    c->h_valid.release();
     c->h_rowstats.release();
     delete c;
 }
@@ -762,14 +769,13 @@ static int detect_args(yb_ctx *c, yb::DetectArgs *out) {
     a.n_reads = c->n_reads;
     a.n_iv = c->n_iv;
     a.max_k = c->max_k;
-    a.n_literal = c->n_literal;
+    a.validate = (!c->validated || c->n_literal) ? 1u : 0u;
     a.rows = c->rows;
     a.cls = c->d_cls.p;
     a.gap_ptr = c->d_gap_ptr.p;
     a.gaps = c->d_gaps.p;
     a.bitmap = c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p;
     a.counters = c->d_counters.p;
-    a.chunk_row = c->d_chunk_row.p;
     a.side_stream = c->side_stream;
     a.ev_fork = c->ev_fork;
     a.ev_join = c->ev_join;
@@ -806,7 +812,7 @@ int yb_upload(yb_ctx *c) {
     if (!c->d_rowptr.reserve(n + 1) || !c->d_len.reserve(n + 1) || !c->d_iv.reserve(m + 2))
         return c->fail(YB_ERR_NOMEM, "device allocation failed (%zu reads, %zu intervals)", n, m);
     if (int rc = ensure_result_buffers(c)) return rc;
-    if (!c->d_rowstats.reserve(1) || !c->h_rowstats.reserve(1) || !c->d_chunk_row.reserve(yb::chunk_table_words(c->n_iv)))
+    if (!c->d_rowstats.reserve(1) || !c->h_rowstats.reserve(1) || !c->h_valid.reserve(4))
         return c->fail(YB_ERR_NOMEM, "allocation failed");
     if (n) {
         YB_CUDA(c, cudaMemcpyAsync(c->d_rowptr.p, c->rowptr_host(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, c->stream));
@@ -814,7 +820,7 @@ int yb_upload(yb_ctx *c) {
     }
     // size classes, big-row scratch needs and input sanity come from one small kernel over rowptr / len; its
     // 128-byte result crosses PCIe while the interval buffer is still on its way
-    const int sl = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->d_chunk_row.p, c->stream);
+    const int sl = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->stream);
     if (sl < 0) return c->cuda_fail(cudaGetLastError(), "row statistics kernel");
     c->stats.kernel_launches += (uint64_t)sl;
     YB_CUDA(c, cudaMemcpyAsync(c->h_rowstats.p, c->d_rowstats.p, sizeof(yb::DevRowStats), cudaMemcpyDeviceToHost, c->stream));
@@ -841,8 +847,8 @@ int yb_upload(yb_ctx *c) {
         c->rows = rs;
         c->max_k = ds.max_k;
     }
-    // behind the interval copy, once per CSR (it cannot change afterwards): 0 <= begin < end <= length for every interval
-    // (rows that fail take the literal heap sweep) and the size-class worklist of the register tier
+    // once per CSR (it cannot change afterwards): the size-class worklist of the register tier. The intervals themselves
+    // are tested by the first detect step.
     const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->rows);
     if (!c->d_scratch.reserve(sb)) return c->fail(YB_ERR_NOMEM, "device scratch allocation failed (%zu bytes)", sb);
     {
@@ -855,16 +861,13 @@ int yb_upload(yb_ctx *c) {
         a.max_k = c->max_k;
         a.rows = c->rows;
         a.counters = c->d_counters.p;
-        a.chunk_row = c->d_chunk_row.p;
         a.scratch = c->d_scratch.p;
         a.scratch_bytes = c->d_scratch.cap;
-        const int ul = yb::launch_upload_kernels(a, c->d_rowstats.p, c->stream);
-        if (ul < 0) return c->cuda_fail(cudaGetLastError(), "upload kernels (validation, worklist)");
+        const int ul = yb::launch_upload_kernels(a, c->stream);
+        if (ul < 0) return c->cuda_fail(cudaGetLastError(), "upload kernels (worklist)");
         c->stats.kernel_launches += (uint64_t)ul;
-        // the validation result travels back now; yb_compute_device reads it (it decides whether literal_kernel runs)
-        YB_CUDA(c, cudaMemcpyAsync(c->h_rowstats.p, c->d_rowstats.p, sizeof(yb::DevRowStats), cudaMemcpyDeviceToHost, c->stream));
         YB_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));
-        c->literal_known = false;
+        c->validated = c->valid_pending = false;
         c->n_literal = c->n_malformed = 0;
     }
     c->stats.h2d_bytes += sizeof(uint32_t) * (2 * n + 1) + sizeof(uint2) * m;
@@ -887,6 +890,7 @@ int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *s
     // synchronises around capture and replay).
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (st != c->stream) cudaStreamIsCapturing(st, &cap);
+    if (st == c->stream) cap = cudaStreamCaptureStatusNone;
     const bool foreign = st != c->stream && cap == cudaStreamCaptureStatusNone;
     int launches;
     if (c->from_report) {
@@ -898,11 +902,12 @@ int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *s
                                        c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p, c->d_counters.p, st);
     } else {
         if (!c->uploaded) return c->fail(YB_ERR_STATE, "yb_compute_device before yb_upload");
-        if (!c->literal_known) {  // the validation kernel's verdict (4 bytes that left the device right behind it)
-            YB_CUDA(c, cudaEventSynchronize(c->ev_upload));
-            c->n_literal = c->h_rowstats.p->malformed_rows;
-            c->n_malformed = c->h_rowstats.p->malformed;
-            c->literal_known = true;
+        if (c->valid_pending && cap == cudaStreamCaptureStatusNone) {  // the verdict of the validating step before this one
+            YB_CUDA(c, cudaEventSynchronize(c->ev_valid));
+            c->n_literal = c->h_valid.p[0];
+            c->n_malformed = c->h_valid.p[1];
+            c->validated = true;
+            c->valid_pending = false;
         }
         if (foreign) {
             YB_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));  // (also covers a download of the previous step)
@@ -911,6 +916,12 @@ int yb_compute_device(yb_ctx *c, uint64_t coverage, double not_coverage, void *s
         yb::DetectArgs a{};
         if (int rc = detect_args(c, &a)) return rc;
         launches = yb::launch_detect(a, coverage > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)coverage, not_coverage, st);
+        if (launches >= 0 && a.validate && cap == cudaStreamCaptureStatusNone && c->n_reads) {  // its two counts follow the step
+            YB_CUDA(c, cudaMemcpyAsync(c->h_valid.p, c->d_counters.p + yb::kCntLiteralLast, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            YB_CUDA(c, cudaMemcpyAsync(c->h_valid.p + 1, c->d_counters.p + yb::kCntMalformedLast, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            YB_CUDA(c, cudaEventRecord(c->ev_valid, st));
+            c->valid_pending = true;
+        }
     }
     if (launches < 0) return c->cuda_fail(cudaGetLastError(), "kernel launch");
     if (foreign) {
@@ -935,8 +946,8 @@ int yb_time_upload_kernels(yb_ctx *c, float *ms_out) {
     int rc = detect_args(c, &a);
     if (rc == YB_OK) {
         cudaEventRecord(e0, c->stream);
-        const int l0 = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->d_chunk_row.p, c->stream);
-        const int l1 = yb::launch_upload_kernels(a, c->d_rowstats.p, c->stream);
+        const int l0 = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->stream);
+        const int l1 = yb::launch_upload_kernels(a, c->stream);
         cudaEventRecord(e1, c->stream);
         if (l0 < 0 || l1 < 0 || cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(ms_out, e0, e1) != cudaSuccess)
             rc = c->cuda_fail(cudaGetLastError(), "upload kernels");
@@ -1037,6 +1048,12 @@ int yb_download(yb_ctx *c) {
     c->stats.n_chimeric = hist[1];
     c->stats.n_not_covered = hist[2];
     c->stats.max_intervals_per_read = c->max_k;
+    if (!c->from_report && n) {  // what the last validating step over this CSR found (copied with the counters)
+        c->n_literal = hc[yb::kCntLiteralLast];
+        c->n_malformed = hc[yb::kCntMalformedLast];
+        c->validated = true;
+        c->valid_pending = false;
+    }
     c->stats.n_malformed_intervals = c->from_report ? 0 : c->n_malformed;
     c->stats.n_literal_reads = c->from_report ? 0 : c->n_literal;
     c->downloaded = true;

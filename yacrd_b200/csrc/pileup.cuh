@@ -35,12 +35,15 @@ constexpr uint32_t kHistSlots = 32;
 // persistent words behind the two sets
 constexpr uint32_t kCntEpoch = 2 * kNumCounters;          // number of detect steps finished on this buffer
 constexpr uint32_t kCntBigList = 2 * kNumCounters + 1;    // upload: rows with more than 512 intervals (big tier)
-constexpr uint32_t kCntLiteralList = 2 * kNumCounters + 2;  // upload: rows with a malformed interval
+constexpr uint32_t kCntLiteralList = 2 * kNumCounters + 2;  // validating step: rows with a malformed interval found so far
+constexpr uint32_t kCntMalformedIv = 2 * kNumCounters + 6;  // validating step: malformed intervals found so far
+constexpr uint32_t kCntLiteralLast = 2 * kNumCounters + 7;  // the two counts of the last finished validating step ...
+constexpr uint32_t kCntMalformedLast = 2 * kNumCounters + 9;  // ... (the closing CTA of order_kernel moves them here)
 constexpr uint32_t kCntScanList = 2 * kNumCounters + 4;     // upload: big rows of the position-scan path
 constexpr uint32_t kCntOrderTimeout = 2 * kNumCounters + 5; // order_kernel: the closing CTA gave up waiting for the others
 constexpr uint32_t kCntPeerTimeoutWait = 2 * kNumCounters + 3;  // peer_wait_kernel gave up (a rank died or never launched)
-constexpr uint32_t kCntClassCursor = 2 * kNumCounters + 8;  // upload: kNumClasses cursors of the worklist scatter
-constexpr uint32_t kCounterWords = 2 * kNumCounters + 8 + 24;
+constexpr uint32_t kCntClassCursor = 2 * kNumCounters + 10;  // upload: kNumClasses cursors of the worklist scatter
+constexpr uint32_t kCounterWords = 2 * kNumCounters + 10 + 24;
 
 
 // Size classes of the register tier: a row with k intervals is sorted by G lanes x kE keys, G the smallest entry of
@@ -113,7 +116,8 @@ struct DetectArgs {
     uint32_t n_reads;
     uint32_t n_iv;
     uint32_t max_k;          // largest row (host knows it from the row pointers)
-    uint32_t n_literal;      // rows with a malformed interval (validate_kernel listed them in the scratch buffer)
+    uint32_t validate;       // 1: the step tests 0 <= begin < end <= length on every interval it loads and hands the rows that
+                             // fail to literal_kernel (the first step after an upload, and every step if that one found any)
     RowStats rows;
     // outputs, resident in HBM
     uint8_t *cls;            // n_reads, yb_read_type
@@ -126,7 +130,6 @@ struct DetectArgs {
     size_t peer_parity_bytes; // n_ranks * slot_bytes: odd steps use the second half of every gather buffer
     uint32_t *peer_flag[16]; // peer p's flag array (word q: steps rank q has finished; word 31: steps this rank has finished)
     uint32_t *counters;      // kCounterWords
-    const uint32_t *chunk_row;  // launch_row_stats: the row every chunk of validate_kernel starts in
     // host side only: a second stream and two events so that the CTA tier (rows with k > 512) runs beside the register
     // tier instead of in front of it (null: same stream, one after the other)
     cudaStream_t side_stream;
@@ -151,17 +154,14 @@ struct DevRowStats {
     uint32_t pad2_[2];
 };
 // Zeroes *out and fills it from the device-resident rowptr / len (one kernel on `stream`). Returns launches or -1.
-// chunk_row (chunk_table_words(n_iv) words): the row every chunk of validate_kernel starts in.
-size_t chunk_table_words(uint32_t n_iv);
-int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, uint32_t *chunk_row, cudaStream_t stream);
+int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream);
 
-// Once per uploaded CSR, behind the interval copy (the CSR cannot change afterwards; both depend on rowptr / len / the
-// intervals only, not on the threshold — the reference builds its read index, a hash map, while it ingests):
-//  * validate_kernel: 0 <= begin < end <= length for every interval; count -> out->malformed, the rows holding one ->
-//    out->malformed_rows and a list in the scratch buffer (launch_detect hands them to the literal heap sweep);
-//  * scatter_kernel: the size-class worklist of the register tier (16 bytes per read: row, first interval, k, class, length).
-// Also zeroes the counter buffer (kCounterWords). a.rows must hold the row statistics. Returns launches or -1.
-int launch_upload_kernels(const DetectArgs &a, DevRowStats *out, cudaStream_t stream);
+// Once per uploaded CSR (it depends on rowptr / len only, not on the threshold - the reference builds its read index, a
+// hash map, while it ingests): scatter_kernel, the size-class worklist of the register tier (16 bytes per read: row,
+// first interval, k, class, length) and the lists of the CTA tier. Also zeroes the counter buffer (kCounterWords).
+// a.rows must hold the row statistics. Returns launches or -1.
+// (The intervals themselves are tested by the first detect step: DetectArgs::validate.)
+int launch_upload_kernels(const DetectArgs &a, cudaStream_t stream);
 
 // Bytes of scratch launch_detect needs for a CSR of this shape.
 size_t detect_scratch_bytes(uint32_t n_reads, uint32_t n_iv, const RowStats &rs);

@@ -192,15 +192,16 @@ __device__ __forceinline__ uint32_t top_bits(uint32_t n) { return n >= 32u ? FUL
 
 // One batch: every in-group lane holds its row's record (all G lanes of a group hold the same one). `refill` issues the
 // next batch's copies into the slab; it is called as soon as this batch's keys are in registers.
-template <int G, bool PK, class Refill>
+template <int G, bool PK, bool VAL, class Refill>
 __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work &w, uint32_t *cnt, WarpSmem &ws, uint2 *buf, const uint4 rec,
                                                 const uint32_t c, uint2 &chunk, const PipeMul pm, const uint32_t lane, Refill refill) {
     using GG = Geo<G>;
     const uint32_t j = lane / (uint32_t)G, g0 = lane % (uint32_t)G;
     const bool in_group = j < (uint32_t)GG::RPB;
     const uint32_t g = in_group ? g0 : 0u;
-    const bool valid = in_group && (rec.z & kRecValid);
+    bool valid = in_group && (rec.z & kRecValid);
     const uint32_t k = valid ? (rec.z & 0xFFFFu) : 0u, len = rec.w;
+    uint32_t nbad = 0;  // VAL: this lane's intervals that violate 0 <= begin < end <= length
     uint2 *slot = buf + (in_group ? j : 0u) * (uint32_t)GG::PITCH + (rec.y & 1u);  // the row's data starts here
     // striped load (conflict-free); the initial arrangement is irrelevant to the sort. Element t * G + g exists iff
     // t * G < k - g; the test is only compiled for slots a row of this class can end in.
@@ -215,6 +216,7 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
             const uint2 v = lane_iv[t * G];
             // (spare lanes - 31 above all - hold +inf for xlane_t when the group is not a power of two)
             const bool absent = (t * G + G - 1 > GG::KMIN && !((uint32_t)(t * G) < left)) || (!GG::kPow2 && !in_group);
+            if (VAL && (PK || ends) && !absent) nbad += !(v.x < v.y && v.y <= len);
             uint32_t key;
             if (!PK) key = ends ? v.y : v.x;
             else if (YB_PACK_IMAD) asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(v.y), "r"(pm.shl16), "r"(v.x));
@@ -226,12 +228,28 @@ __device__ __forceinline__ void process_batch_t(const DetectArgs &a, const Work 
     // element kE l + t - c - 1 is then T[(t - c - 1) % kE][l + floor((t - c - 1) / kE)], a warp-uniform offset from the
     // lane's own column: conflict-free writes and reads, no per-element index arithmetic
     uint32_t *T = ws.scr + 1u + lane;
+    auto validated = [&]() {
+        // A validating step (the first one after an upload): a row with a malformed interval is not this kernel's business,
+        // the closed form is only the reference's heap sweep for well-formed rows. It goes on the list of literal_kernel.
+        if (!valid) nbad = 0;
+        const uint32_t bb = __ballot_sync(FULL, nbad != 0u);
+        if (bb) {  // rare
+            const uint32_t gmask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << (lane - g));
+            if (nbad) atomicAdd(a.counters + kCntMalformedIv, nbad);
+            if (valid && (bb & gmask)) {
+                if (g == 0u) w.lit_list[atomicAdd(a.counters + kCntLiteralList, 1u)] = rec.x;
+                valid = false;
+            }
+        }
+    };
     if (PK) {
         load_keys(false);
         refill();
+        if (VAL) validated();
         sort_group_t<G, PK>(K0, lane, g, in_group, pm);
     } else {
         load_keys(true);
+        if (VAL) validated();
         sort_group_t<G, PK>(K0, lane, g, in_group, pm);
     }
     __syncwarp();
