@@ -112,8 +112,7 @@ struct Work {
     uint2 *meta;                     // n_reads: {where the row's bad regions sit in `stage` (pairs), how many}
     uint2 *stage;                    // bad regions in batch-completion order (warps reserve chunks with one atomic)
     uint32_t stage_cap;              // pairs
-    uint32_t *part_total;            // n_parts: bad regions of every part of kPartRows rows (totals_kernel)
-    uint32_t *part_prefix;           // their exclusive prefix (the last CTA of totals_kernel)
+    unsigned long long *part_desc;   // n_parts: step tag << 32 | bad regions of the part (order_kernel publishes, later parts sum)
     uint32_t n_parts;
     uint32_t *lit_list;              // rows holding a malformed interval, found by a validating step (they take the literal heap sweep)
     uint32_t *big_list;              // rows with k > kSmallMaxK that are sorted by a CTA
@@ -673,38 +672,50 @@ __device__ __forceinline__ uint32_t push_le(uint32_t m, uint32_t ev, uint32_t q)
     return r;
 }
 
-// Lane geometry of a batch of class G: rows_per_batch groups of G consecutive lanes.
-struct LaneGeo {
-    uint32_t G, rpb, j, g;  // lanes per row, rows per batch, this lane's row slot and index in the group
-    bool in_group;
-};
-__device__ __forceinline__ LaneGeo lane_geo(const ClassTab &tab, uint32_t cls, uint32_t lane) {
-    LaneGeo x;
-    x.G = tab.lanes[cls];
-    x.rpb = tab.rpb[cls];
-    x.j = (lane * tab.inv[cls]) >> 16;  // lane / G
-    x.g = lane - x.j * x.G;
-    x.in_group = x.j < x.rpb;
-    if (!x.in_group) x.g = 0;
-    return x;
-}
-
 #include "regtier.cuh"
+
+// The class a warp's batch indices currently fall in, held in registers: indices drawn by a warp only grow, so the class
+// table (kernel parameter, i.e. constant bank with a run-time index: a chain of slow loads) is read once per class, not
+// once per batch.
+struct ClassCursor {
+    uint32_t q, lo, hi;  // position in processing order; batches [lo, hi) belong to it
+    uint32_t cls, G, rpb, inv, ebase, count;
+};
+__device__ __forceinline__ void cursor_load(const ClassTab &tab, ClassCursor &cu) {
+    cu.lo = tab.item_base[cu.q];
+    cu.hi = tab.item_base[cu.q + 1];
+    cu.cls = tab.order[cu.q];
+    cu.G = tab.lanes[cu.cls];
+    cu.rpb = tab.rpb[cu.cls];
+    cu.inv = tab.inv[cu.cls];
+    cu.ebase = tab.entry_base[cu.cls];
+    cu.count = tab.count[cu.cls];
+}
 
 // Starts the copy of this lane's record of batch `item` (the record of the row its group sorts) into the warp's
 // shared-memory slot: cp.async, global -> shared without a register in between, so nothing has to stay live (or be
-// spilled, which would wait for the load) across the batch being sorted. Lanes without a row get a zero record.
-__device__ __forceinline__ void fetch_rec(const Work &w, const ClassTab &tab, uint4 *slot, uint32_t item, uint32_t n_items, uint32_t &q,
-                                          uint32_t &cls, uint32_t lane) {
+// spilled, which would wait for the load) across the batch being sorted. Lanes without a row get a zero record. Beside
+// it goes the lane's place in the batch for issue_batch: where its row's slab starts in the buffer, and (top bit)
+// whether this lane is the first of its group.
+__device__ __forceinline__ void fetch_rec(const Work &w, const ClassTab &tab, ClassCursor &cu, uint4 *slot, uint32_t *geo_slot, uint32_t item,
+                                          uint32_t n_items, uint32_t &cls, uint32_t lane) {
     cls = 0;
     const uint4 *src = nullptr;
+    uint32_t geo = 0;
     if (item < n_items) {
-        while (item >= tab.item_base[q + 1]) ++q;
-        cls = tab.order[q];
-        const LaneGeo geo = lane_geo(tab, cls, lane);
-        const uint32_t e = (item - tab.item_base[q]) * geo.rpb + geo.j;
-        if (geo.in_group && e < tab.count[cls]) src = w.recs + tab.entry_base[cls] + e;
+        while (item >= cu.hi) {
+            ++cu.q;
+            cursor_load(tab, cu);
+        }
+        cls = cu.cls;
+        const uint32_t j = (lane * cu.inv) >> 16, g = lane - j * cu.G;  // lane / G, lane % G
+        if (j < cu.rpb) {
+            const uint32_t e = (item - cu.lo) * cu.rpb + j;
+            if (e < cu.count) src = w.recs + cu.ebase + e;
+            geo = j * ((uint32_t)kE * cu.G + 2u) | (g == 0u ? 0x80000000u : 0u);
+        }
     }
+    geo_slot[lane] = geo;
     if (src) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(slot + lane)), "l"(src) : "memory");
     else slot[lane] = make_uint4(0, 0, 0, 0);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -712,25 +723,19 @@ __device__ __forceinline__ void fetch_rec(const Work &w, const ClassTab &tab, ui
 __device__ __forceinline__ void fetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // TMA copies of the batch's row slabs into `buf` (one per row, issued by the group's first lane).
-__device__ __forceinline__ void issue_batch(const DetectArgs &a, const ClassTab &tab, uint2 *buf, unsigned long long *bar,
-                                            const uint4 rec, uint32_t cls, uint32_t lane) {
-    const LaneGeo geo = lane_geo(tab, cls, lane);
+__device__ __forceinline__ void issue_batch(const DetectArgs &a, uint2 *buf, unsigned long long *bar, const uint4 rec, const uint32_t geo,
+                                            uint32_t lane) {
     uint32_t bytes = 0, cs = 0;
-    if (geo.in_group && geo.g == 0u && (rec.z & kRecValid)) {
+    if ((geo >> 31) && (rec.z & kRecValid)) {
         cs = rec.y & ~1u;
         bytes = (((rec.y + (rec.z & 0xFFFFu) + 1u) & ~1u) - cs) * 8u;
     }
     const uint32_t total = __reduce_add_sync(FULL, bytes);
     if (lane == 0) mbar_expect_tx(bar, total);
     __syncwarp();
-    if (bytes) tma_load_1d(buf + geo.j * ((uint32_t)kE * geo.G + 2u), a.iv + cs, bytes, bar);
+    if (bytes) tma_load_1d(buf + (geo & 0x7FFFFFFFu), a.iv + cs, bytes, bar);
 }
 
-// sort_kernel: ONE persistent CTA per SM; its warps run on their own (no barrier after the prologue). Batches are dealt
-// to the CTAs round-robin (CTA b takes batches b, b + gridDim, ...: every SM sees the same mix of classes) and drawn
-// inside a CTA from a shared-memory counter: a global counter would cost every warp an L2 round trip per batch, because
-// ptxas turns any atomic in a divergent region into a warp-aggregated one whose result is broadcast by a shuffle on the
-// spot (no way to keep it in flight behind a batch).
 template <bool VAL>
 __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Work w, ClassTab tab, uint32_t c, PipeMul pm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -747,7 +752,9 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
     const uint32_t n_items = tab.item_base[kNumClasses];
-    uint32_t q = 0;
+    ClassCursor cu;
+    cu.q = 0;
+    cursor_load(tab, cu);
 #ifdef YB_STATIC_SCHED
     uint32_t local_next = wid;
     auto draw_raw = [&]() {  // fixed deal inside the CTA as well: warp w takes the CTA's batches w, w + WARPS, ...
@@ -770,12 +777,12 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
     // software pipeline: the record of batch i+2 is on its way to shared memory, the slab copies of batch i+1 are issued
     // as soon as the keys of batch i are in registers (one slab buffer) and land while batch i is sorted
     uint32_t cls0, cls1, cls2, s = 1;  // ws.rec[s]: record of batch i+1; ws.rec[s ^ 1]: of batch i+2
-    fetch_rec(w, tab, ws.rec[0], item, n_items, q, cls0, lane);
-    fetch_rec(w, tab, ws.rec[1], item1, n_items, q, cls1, lane);
+    fetch_rec(w, tab, cu, ws.rec[0], ws.geo[0], item, n_items, cls0, lane);
+    fetch_rec(w, tab, cu, ws.rec[1], ws.geo[1], item1, n_items, cls1, lane);
     fetch_wait();
     uint4 rec0 = ws.rec[0][lane];
-    if (item < n_items) issue_batch(a, tab, buf, &ws.mbar, rec0, cls0, lane);
-    fetch_rec(w, tab, ws.rec[0], item2, n_items, q, cls2, lane);
+    if (item < n_items) issue_batch(a, buf, &ws.mbar, rec0, ws.geo[0][lane], lane);
+    fetch_rec(w, tab, cu, ws.rec[0], ws.geo[0], item2, n_items, cls2, lane);
     uint32_t parity = 0;
     uint2 chunk = make_uint2(0, 0);  // [next free pair, end) of the warp's staging chunk
     while (item < n_items) {
@@ -786,7 +793,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
             // this batch's generic-proxy reads of the slab before the async-proxy writes of the next batch's copies
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (item1 < n_items) issue_batch(a, tab, buf, &ws.mbar, ws.rec[s][lane], cls1, lane);
+            if (item1 < n_items) issue_batch(a, buf, &ws.mbar, ws.rec[s][lane], ws.geo[s][lane], lane);
         };
 #define YB_CASE(gi)                                                                                                        \
     case gi: process_batch_t<class_lanes_c(gi), true, VAL>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;        \
@@ -806,7 +813,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
         item = item1;
         item1 = item2;
         item2 = draw_done(raw3);
-        fetch_rec(w, tab, ws.rec[s], item2, n_items, q, cls2, lane);
+        fetch_rec(w, tab, cu, ws.rec[s], ws.geo[s], item2, n_items, cls2, lane);
         s ^= 1u;
         parity ^= 1u;
     }
@@ -815,64 +822,36 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
 constexpr size_t kSortSmemBytes = kWarpSmemBytes * kSortWarps;
 
 // ------------------------------------------------------------------------------------------------
-// ordering pass: the sorting kernels left, per row, a staging offset and a count. totals_kernel sums the counts of every
-// part of 1024 rows (one warp per part: a few microseconds; a RED per row from the sorting kernels would serialise in L2,
-// because at any moment every warp of the GPU works on the same stretch of rows). order_kernel then takes one part per
-// CTA, 4 consecutive rows per thread, with no ordering between CTAs: it sums the totals of the parts before it (at most
-// a couple of thousand words), turns counts into offsets (thread-local prefix + block scan), moves the staged regions to
-// their final place, classifies (editor/mod.rs:85-100) and writes the 2-bit bitmap (to every peer's gather buffer when
-// the all-gather is fused in). The CTA of the last part closes the step once the others are through: it zeroes the other
-// counter set, bumps the step number and, with peers, tells every rank that this rank's slot is complete.
+// ordering pass (order_kernel, the second and last kernel of a detect step): the sorting kernels left, per row, a
+// staging offset and a count. A CTA takes one part of 2048 rows (in ticket order), 4 consecutive rows per thread: it
+// publishes the part's total in one 64-bit word tagged with the step number (never reset) as soon as its counts are
+// loaded, sums the totals of ALL parts before it (a thousand words at most; it only ever waits for parts that are
+// already running and whose total does not depend on anybody: no scan kernel, no look-back chain, and no RED per row
+// in the sorting kernels, which serialised in L2 when every warp of the GPU worked on the same stretch of rows), turns
+// counts into offsets (thread-local prefix + block scan), moves the staged regions to their final place, classifies
+// (editor/mod.rs:85-100) and writes the 2-bit bitmap (to every peer's gather buffer when the all-gather is fused in).
+// The last CTA to finish closes the step: it zeroes the other counter set, bumps the step number and, with peers, tells
+// every rank that this rank's slot is complete.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) totals_kernel(DetectArgs a, Work w) {
-    __shared__ uint32_t s_last, s_w[8];
-    const uint32_t tid = threadIdx.x, lane = lane_id(), wid = tid >> 5, part = (blockIdx.x * blockDim.x + tid) >> 5;
-    const uint32_t ep = __ldcg(a.counters + kCntEpoch);
-    uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
-    if (part < w.n_parts) {
-        const uint32_t r0 = part * kPartRows, r1 = min(r0 + kPartRows, a.n_reads);
-        uint32_t sum = 0;
-        for (uint32_t r = r0 + 2u * lane; r < r1; r += 64u) {  // two 8-byte records per load
-            if (r + 1u < r1) {
-                const uint4 x = *reinterpret_cast<const uint4 *>(w.meta + r);
-                sum += x.y + x.w;
-            } else {
-                sum += w.meta[r].y;
-            }
-        }
-        sum = __reduce_add_sync(FULL, sum);
-        if (lane == 0) w.part_total[part] = sum;
-    }
-    // the last CTA out turns the totals into their exclusive prefix (order_kernel's CTAs read one word each)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(cnt + kCntTotalsDone, 1u) == gridDim.x - 1u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const uint32_t n = w.n_parts, per = (n + 255u) / 256u, beg = min(tid * per, n), end = min(beg + per, n);
-    uint32_t s = 0;
-    for (uint32_t i = beg; i < end; ++i) s += __ldcg(w.part_total + i);
-    const uint32_t incl = warp_incl_scan(s);
-    if (lane == 31u) s_w[wid] = incl;
-    __syncthreads();
-    uint32_t run = incl - s;
-#pragma unroll
-    for (uint32_t q = 0; q < 8u; ++q) run += q < wid ? s_w[q] : 0u;
-    for (uint32_t i = beg; i < end; ++i) {
-        const uint32_t t = __ldcg(w.part_total + i);
-        w.part_prefix[i] = run;
-        run += t;
-    }
+__device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_kernel(DetectArgs a, Work w, double not_cov) {
+#ifndef YB_ORDER_MIN_CTAS
+#define YB_ORDER_MIN_CTAS (1024 / YB_ORDER_THREADS)
+#endif
+__global__ void __launch_bounds__(kOrderThreads, YB_ORDER_MIN_CTAS) order_kernel(DetectArgs a, Work w, double not_cov) {
     constexpr uint32_t R = kOrderRows, NW = kOrderThreads / 32;
-    __shared__ uint32_t s_warp[NW], s_hist[NW];
+    __shared__ uint32_t s_warp[NW], s_pre[NW], s_hist[NW], s_last, s_part;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
-    const uint32_t part = blockIdx.x, r0 = part * kPartRows + tid * R;
+    if (tid == 0) s_part = atomicAdd(cnt + kCntTicket, 1u);  // parts start in ticket order: a part only waits for parts that run
     uint32_t peer_step = 0;
     if (a.n_peers) {
         // every rank has finished step peer_step - 1 (and, in its stream order, whatever read the gather buffer of step
@@ -889,30 +868,25 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
             if ((int32_t)(seen - peer_step) < 0) atomicAdd(cnt + kCntPeerTimeout, 1u);
         }
     }
+    __syncthreads();
+    const uint32_t part = s_part, r0 = part * kPartRows + tid * R;
     // everything the rows need is requested up front; the first two regions of a row (most have <= 3) ride along
-    const uint32_t pre = __ldg(w.part_prefix + part);  // regions of the parts before this one
     uint2 m[R];
     uint32_t l[R];
     const bool full = r0 + R <= a.n_reads;
     if (full) {
-        if (R == 1) {
-            m[0] = w.meta[r0];
-            l[0] = __ldg(a.len + r0);
-        } else {
-            const uint4 *mp = reinterpret_cast<const uint4 *>(w.meta + r0);
+        const uint4 *mp = reinterpret_cast<const uint4 *>(w.meta + r0);
+        const uint4 *lp = reinterpret_cast<const uint4 *>(a.len + r0);
 #pragma unroll
-            for (uint32_t i = 0; i < R / 2; ++i) {
-                const uint4 x = mp[i];
-                m[2 * i] = make_uint2(x.x, x.y);
-                m[(2 * i + 1) % R] = make_uint2(x.z, x.w);
-            }
-            if (R == 2) {
-                const uint2 x = __ldg(reinterpret_cast<const uint2 *>(a.len + r0));
-                l[0] = x.x, l[1 % R] = x.y;
-            } else {
-                const uint4 x = __ldg(reinterpret_cast<const uint4 *>(a.len + r0));
-                l[0] = x.x, l[1 % R] = x.y, l[2 % R] = x.z, l[3 % R] = x.w;
-            }
+        for (uint32_t i = 0; i < R / 2; ++i) {
+            const uint4 x = mp[i];
+            m[2 * i] = make_uint2(x.x, x.y);
+            m[2 * i + 1] = make_uint2(x.z, x.w);
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < R / 4; ++i) {
+            const uint4 x = __ldg(lp + i);
+            l[4 * i] = x.x, l[4 * i + 1] = x.y, l[4 * i + 2] = x.z, l[4 * i + 3] = x.w;
         }
     } else {
 #pragma unroll
@@ -935,9 +909,30 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
     const uint32_t incl = warp_incl_scan(mine);
     if (lane == 31u) s_warp[wid] = incl;
     __syncthreads();
-    uint32_t gp = pre + incl - mine;
+    const unsigned long long tag = (unsigned long long)(ep + 1u) << 32;
+    if (tid == 0) {  // the part's total, for the parts behind this one
+        uint32_t tot = 0;
 #pragma unroll
-    for (uint32_t q = 0; q < NW; ++q) gp += q < wid ? s_warp[q] : 0u;
+        for (uint32_t q = 0; q < NW; ++q) tot += s_warp[q];
+        st_desc(w.part_desc + part, tag | tot);
+    }
+    uint32_t pre = 0;  // totals of the parts before this one (they hold earlier tickets: running or done)
+    for (uint32_t i0 = tid; i0 < part; i0 += 8u * kOrderThreads) {  // eight loads in flight per thread, the stragglers polled
+        unsigned long long d[8];
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; ++u) d[u] = i0 + u * kOrderThreads < part ? ld_desc(w.part_desc + i0 + u * kOrderThreads) : tag;
+#pragma unroll
+        for (uint32_t u = 0; u < 8u; ++u) {
+            while ((d[u] >> 32) != (tag >> 32)) d[u] = ld_desc(w.part_desc + i0 + u * kOrderThreads);
+            pre += (uint32_t)d[u];
+        }
+    }
+    pre = __reduce_add_sync(FULL, pre);
+    if (lane == 0u) s_pre[wid] = pre;
+    __syncthreads();
+    uint32_t gp = incl - mine;
+#pragma unroll
+    for (uint32_t q = 0; q < NW; ++q) gp += s_pre[q] + (q < wid ? s_warp[q] : 0u);
     if (tid == kOrderThreads - 1u && part == w.n_parts - 1u) a.gap_ptr[a.n_reads] = gp + mine;
     uint32_t off[R], cl[R], h1 = 0, h2 = 0, bits = 0;
 #pragma unroll
@@ -967,9 +962,12 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
         h2 += cl[i] == 2u;
         bits |= cl[i] << (2u * i);
     }
-    if (full && R == 4) {
-        *reinterpret_cast<uint4 *>(a.gap_ptr + r0) = make_uint4(off[0], off[1 % R], off[2 % R], off[3 % R]);
-        *reinterpret_cast<uint32_t *>(a.cls + r0) = cl[0] | cl[1 % R] << 8 | cl[2 % R] << 16 | cl[3 % R] << 24;
+    if (full) {
+        uint4 *gpp = reinterpret_cast<uint4 *>(a.gap_ptr + r0);
+#pragma unroll
+        for (uint32_t i = 0; i < R / 4; ++i) gpp[i] = make_uint4(off[4 * i], off[4 * i + 1], off[4 * i + 2], off[4 * i + 3]);
+        static_assert(R == 4, "class codes of a thread's rows go out as one 4-byte store");
+        *reinterpret_cast<uint32_t *>(a.cls + r0) = cl[0] | cl[1] << 8 | cl[2] << 16 | cl[3] << 24;
     } else {
 #pragma unroll
         for (uint32_t i = 0; i < R; ++i)
@@ -978,12 +976,11 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
                 a.cls[r0 + i] = (uint8_t)cl[i];
             }
     }
-    // 16 / R threads (16 rows) make one 32-bit word of the 2-bit bitmap
-    constexpr uint32_t TPW = 16u / R;
-    uint32_t word = bits << (2u * R * (lane & (TPW - 1u)));
-#pragma unroll
-    for (uint32_t o = 1; o < TPW; o <<= 1) word |= __shfl_xor_sync(FULL, word, o);
-    if ((lane & (TPW - 1u)) == 0u && r0 < a.n_reads) {
+    // four threads (16 rows) make one 32-bit word of the 2-bit bitmap
+    uint32_t word = bits << (8u * (lane & 3u));
+    word |= __shfl_xor_sync(FULL, word, 1);
+    word |= __shfl_xor_sync(FULL, word, 2);
+    if ((lane & 3u) == 0u && r0 < a.n_reads) {
         if (a.n_peers == 0u) {
             reinterpret_cast<uint32_t *>(a.bitmap)[r0 >> 4] = word;
         } else {  // all-gather fused into the epilogue: the word goes to this rank's slot on every rank (NVLink stores);
@@ -1007,42 +1004,29 @@ __global__ void __launch_bounds__(kOrderThreads, 1024 / kOrderThreads) order_ker
         if (n_live - c1 - c2) atomicAdd(slot + 0, n_live - c1 - c2);
         if (c1) atomicAdd(slot + 1, c1);
         if (c2) atomicAdd(slot + 2, c2);
+        __threadfence();
+        s_last = atomicAdd(cnt + kCntDone, 1u) == w.n_parts - 1u;
     }
-    // the CTA of the last part closes the step once every other CTA is through (they leave one RED behind and go): next
-    // step's counter set, step number, peers
-    if (part != w.n_parts - 1u) {
+    __syncthreads();
+    if (s_last) {  // the step is complete: next step's counter set, step number, peers
+        uint32_t *other = a.counters + ((ep + 1u) & 1u) * kNumCounters;
+        for (uint32_t i = tid; i < kNumCounters; i += kOrderThreads) other[i] = 0u;
         __threadfence();
         __syncthreads();
-        if (tid == 0) atomicAdd(cnt + kCntDone, 1u);
-        return;
-    }
-    if (tid == 0) {
-        uint32_t seen = 0;
-        for (uint32_t spin = 0; spin < (1u << 24); ++spin) {  // bounded: a CTA that died must not hang the GPU
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt + kCntDone) : "memory");
-            if (seen >= w.n_parts - 1u) break;
-            __nanosleep(100);
+        if (tid == 0) {
+            a.counters[kCntEpoch] = ep + 1u;
+            if (a.validate) {  // what this step's validation found, for the host; the running counts start over
+                a.counters[kCntLiteralLast] = a.counters[kCntLiteralList];
+                a.counters[kCntMalformedLast] = a.counters[kCntMalformedIv];
+                a.counters[kCntLiteralList] = 0u;
+                a.counters[kCntMalformedIv] = 0u;
+            }
         }
-        if (seen < w.n_parts - 1u) atomicAdd(a.counters + kCntOrderTimeout, 1u);
-    }
-    __syncthreads();
-    uint32_t *other = a.counters + ((ep + 1u) & 1u) * kNumCounters;
-    for (uint32_t i = tid; i < kNumCounters; i += kOrderThreads) other[i] = 0u;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        a.counters[kCntEpoch] = ep + 1u;
-        if (a.validate) {  // what this step's validation found, for the host; the running counts start over
-            a.counters[kCntLiteralLast] = a.counters[kCntLiteralList];
-            a.counters[kCntMalformedLast] = a.counters[kCntMalformedIv];
-            a.counters[kCntLiteralList] = 0u;
-            a.counters[kCntMalformedIv] = 0u;
+        if (a.n_peers) {
+            __threadfence_system();  // every part's peer stores (fenced by their writers before kCntDone) before the flags
+            if (tid < a.n_peers) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flag[tid] + a.rank), "r"(peer_step + 1u) : "memory");
+            if (tid == 0) a.peer_flag[a.rank][31] = peer_step + 1u;
         }
-    }
-    if (a.n_peers) {
-        __threadfence_system();  // every part's peer stores (fenced by their writers before kCntDone) before the flags
-        if (tid < a.n_peers) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flag[tid] + a.rank), "r"(peer_step + 1u) : "memory");
-        if (tid == 0) a.peer_flag[a.rank][31] = peer_step + 1u;
     }
 }
 
@@ -1274,8 +1258,7 @@ Work carve(const DetectArgs &a, uint64_t huge_keys, uint64_t n_big, size_t *tota
     const uint64_t cap = (uint64_t)a.n_iv + a.n_reads + ((uint64_t)a.n_iv + a.n_reads) / 2 + 2ull * a.n_reads + 4096ull * kStageChunk;  // + one open chunk per resident warp
     w.stage_cap = cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cap;
     w.stage = reinterpret_cast<uint2 *>(take(sizeof(uint2) * ((size_t)w.stage_cap + 1)));
-    w.part_total = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)w.n_parts + 8)));
-    w.part_prefix = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * ((size_t)w.n_parts + 8)));
+    w.part_desc = reinterpret_cast<unsigned long long *>(take(sizeof(unsigned long long) * ((size_t)w.n_parts + 8)));
     w.big_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.scan_list = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (n_big + 1)));
     w.huge_keys = reinterpret_cast<uint32_t *>(take(sizeof(uint32_t) * (huge_keys + 1)));
@@ -1363,6 +1346,7 @@ int launch_upload_kernels(const DetectArgs &a, cudaStream_t stream) {
     size_t total = 0;
     Work w = carve(a, a.rows.huge_keys, a.rows.n_big, &total);
     if (total > a.scratch_bytes) return -1;
+    if (cudaMemsetAsync(w.part_desc, 0, sizeof(unsigned long long) * (size_t)w.n_parts, stream) != cudaSuccess) return -1;
     scatter_kernel<<<(a.n_reads + kScatterRows - 1u) / kScatterRows, kScatterRows, 0, stream>>>(a, w, make_plan(a));
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
@@ -1433,9 +1417,7 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         literal_kernel<<<(uint32_t)dc->n_sm, 64, 0, stream>>>(a, w, coverage);
         ++launches;
     }
-    totals_kernel<<<(w.n_parts + 7u) / 8u, 256, 0, stream>>>(a, w);
     order_kernel<<<w.n_parts, kOrderThreads, 0, stream>>>(a, w, not_coverage);
-    ++launches;
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;

@@ -23,7 +23,7 @@ enum Counter : uint32_t {
     kCntTileWide = 5,    // the same for the long reads' kernel
     kCntHugeBump = 6,    // bump allocator (in u32 keys) of the global-scratch tier
     kCntStage = 11,      // bump allocator (in pairs) of the bad-region staging buffer
-    kCntTotalsDone = 13, // totals_kernel: CTAs finished (the last one scans the part totals)
+    kCntTicket = 13,     // order_kernel: dynamic part index (a part only waits for parts that already run)
     kCntStageOverflow = 14,  // rows whose bad regions did not fit the staging buffer (must stay 0)
     kCntPeerTimeout = 15,  // a peer never signalled the previous step (a rank died or never launched)
     kCntDone = 16,       // order_kernel: parts finished (the last one closes the step)

@@ -30,7 +30,7 @@ constexpr uint32_t kScrWords2 = (uint32_t)kE * kScrPitch2 + 4u;
 #define YB_FMA_CE_MOD 0  // n > 0: every n-th in-lane compare-exchange computes its max as a + b - min with two IMADs (FMA pipe)
 #endif
 #ifndef YB_PACK_IMAD
-#define YB_PACK_IMAD 0   // 1: begin | end << 16 and (begin << 16 | 0xFFFF) as IMADs instead of PRMTs
+#define YB_PACK_IMAD 1   // 1: begin | end << 16 and (begin << 16 | 0xFFFF) as IMADs (FMA pipe) instead of PRMTs (ALU pipe, the busy one)
 #endif
 
 template <int G> struct Geo {
@@ -172,6 +172,7 @@ struct alignas(16) WarpSmem {  // one per warp: a warp runs on its own, no CTA-w
     unsigned long long mbar;
     unsigned long long pad_;
     uint4 rec[2][32];  // worklist records of the next two batches, one per lane (cp.async)
+    uint32_t geo[2][32];  // and the lanes' places in those batches (fetch_rec)
     uint32_t scr[kScrWords2];
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "the slab must stay 16-byte aligned");
