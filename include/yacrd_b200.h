@@ -143,6 +143,14 @@ int64_t yb_read_index(const yb_ctx *ctx, const char *id, size_t id_len); /* -1 w
  * host CSR -> H2D -> sm_100a kernels -> D2H of classes + bad-region lists. `coverage` is `-c`
  * (cli.rs:49-51), `not_coverage` is `-n` (cli.rs:53-55). */
 int yb_compute_all_bad_part(yb_ctx *ctx, uint64_t coverage, double not_coverage);
+/* Streamed batches: the reference's `-d/--ondisk` mode (reads2ovl/ondisk.rs, cli.rs:61-70) bounds the working set by
+ * flushing its overlap store every --ondisk-buffer-size bytes; here the bound applies to the device and buys overlap.
+ * With n_intervals > 0, yb_compute_all_bad_part sends a CSR with more intervals than that through the device in chunks of
+ * whole reads (about n_intervals intervals each, a multiple of 1024 reads) on two lanes, each with its own stream and
+ * device buffers of chunk size: chunk k + 1 crosses PCIe while chunk k is computed and the results of chunk k - 1 come
+ * back. Results, getters and statistics are the same as for the one-shot call (bit-identical). 0 (default) = one shot.
+ * Not combined with yb_upload / yb_bind_peers / yb_bind_device_bitmap (those keep the one-shot path). */
+int yb_set_chunk_intervals(yb_ctx *ctx, uint32_t n_intervals);
 /* get_bad_part, stack.rs:164-169: unknown id => YB_OK with n_gaps = 0, length = 0, cls = NotBad. */
 int yb_get_bad_part(yb_ctx *ctx, const char *id, size_t id_len, const uint32_t **gap_pairs,
                     uint32_t *n_gaps, uint64_t *length, uint8_t *cls);
@@ -226,6 +234,10 @@ int yb_get_stats(yb_ctx *ctx, yb_stats *out);
 /* Measurement aid: runs the once-per-upload kernels (row statistics, interval validation, size-class worklist) again on
  * the resident CSR and returns their device time (CUDA events) in milliseconds. Results of an earlier step are dropped. */
 int yb_time_upload_kernels(yb_ctx *ctx, float *ms_out);
+/* The device side of a one-shot call on the uploaded CSR, timed with CUDA events on the context's stream: the per-upload
+ * kernels again (as yb_time_upload_kernels) and then the first detect step, the one that also tests every interval. The
+ * step's results are left for yb_download. With peers bound every rank must make the call (the step all-gathers). */
+int yb_time_one_shot(yb_ctx *ctx, uint64_t coverage, double not_coverage, float *ms_upload_kernels, float *ms_first_step);
 
 /* ---- synthetic workload generator (BASELINE.json configs). Host only. ---------- */
 typedef struct yb_synth_spec {

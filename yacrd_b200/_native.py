@@ -103,6 +103,8 @@ SIGNATURES = {
     "yb_bind_peers": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _sz]),
     "yb_peer_wait": (C.c_int, [_vp, _vp]),
     "yb_time_upload_kernels": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "yb_set_chunk_intervals": (C.c_int, [_vp, C.c_uint32]),
+    "yb_time_one_shot": (C.c_int, [_vp, C.c_uint64, C.c_double, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "yb_synth_paf": (C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint64, _vp, C.c_uint64]),
     "yb_synth_fill": (C.c_int, [C.POINTER(YbSynthSpec), _vp, _vp, _vp, C.c_uint32, _vp, C.c_int]),
 }

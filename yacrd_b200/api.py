@@ -99,6 +99,17 @@ class Context:
     def compute_all(self, coverage, not_coverage):
         self._ck(self._L.yb_compute_all_bad_part(self._h, int(coverage), float(not_coverage)))
 
+    def set_chunk_intervals(self, n_intervals):
+        """Streamed batches (the reference's --ondisk-buffer-size, in intervals): compute_all sends a larger CSR through
+        the device in chunks, transfers overlapped with the kernels. 0 = one shot."""
+        self._ck(self._L.yb_set_chunk_intervals(self._h, int(n_intervals)))
+
+    def time_one_shot(self, coverage, not_coverage):
+        """-> (ms of the per-upload kernels, ms of the first, validating detect step) on the uploaded CSR."""
+        a, b = C.c_float(), C.c_float()
+        self._ck(self._L.yb_time_one_shot(self._h, int(coverage), float(not_coverage), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def time_upload_kernels(self):
         """Device milliseconds of the once-per-upload kernels (row statistics, validation, worklist), re-run on the resident CSR."""
         ms = C.c_float(0)

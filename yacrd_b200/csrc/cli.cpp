@@ -6,11 +6,14 @@
 // exactly as main.rs drives its trait objects: init (main.rs:57) -> compute_all_bad_part (main.rs:78) -> one report
 // line per read (main.rs:80-84) -> the optional editor subcommand (main.rs:87-117):
 //   yacrd-b200 -i overlaps.paf -o report.yacrd scrubb|filter|extract|split -i reads.fastq -o edited.fastq
-// `-d/--ondisk` is accepted for compatibility: the device path keeps the batch resident, so the on-disk store is not used.
+// `-d/--ondisk` selects streamed batches: the reference bounds its working set by flushing the overlap store to disk every
+// --ondisk-buffer-size bytes (cli.rs:61-70); here the input goes through the device in chunks of that many bytes of
+// intervals (8 bytes each), transfers overlapped with the kernels. The prefix itself is not used: nothing goes to disk.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -31,8 +34,9 @@ void usage(FILE *f) {
             "    -n, --not-coverage <NOT_COVERAGE>   bad-length / length above which a read is NotCovered [default: 0.8]\n"
             "    -t, --thread <THREADS>              host threads of the parser, 0 = all [default: all]\n"
             "        --read-buffer-size <SIZE>       read buffer of the parser [default: 8192]\n"
-            "    -d, --ondisk <PREFIX>               accepted and ignored (the batch stays resident on the device)\n"
-            "        --ondisk-buffer-size <SIZE>     accepted and ignored\n"
+            "    -d, --ondisk <PREFIX>               streamed batches: chunks of --ondisk-buffer-size bytes of intervals go\n"
+            "                                        through the device, transfers overlapped (nothing is written to disk)\n"
+            "        --ondisk-buffer-size <SIZE>     bytes of intervals per chunk with -d [default: 64000000]\n"
             "        --device <N>                    CUDA device ordinal [default: current]\n"
             "        --timing                        phase times on stderr\n"
             "    -h, --help    -V, --version\n\n"
@@ -61,7 +65,8 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 int main(int argc, char **argv) {
     std::string input, output, sub_input, sub_output;
     int subcmd = -1;  // yb_editor
-    uint64_t coverage = 0, threads = 0, buffer_size = 8192, dummy;
+    uint64_t coverage = 0, threads = 0, buffer_size = 8192, ondisk_buffer_size = 64000000;
+    bool ondisk = false;
     double not_coverage = 0.8;
     int device = -1;
     bool timing = false;
@@ -109,9 +114,12 @@ int main(int argc, char **argv) {
             }
         } else if (a == "-d" || a == "--ondisk") {
             value("--ondisk");
-            fprintf(stderr, "note: --ondisk is ignored, the device path keeps the batch resident\n");
+            ondisk = true;
         } else if (a == "--ondisk-buffer-size") {
-            parse_u64(value("--ondisk-buffer-size"), &dummy);
+            if (!parse_u64(value("--ondisk-buffer-size"), &ondisk_buffer_size)) {
+                fprintf(stderr, "error: Invalid value for '--ondisk-buffer-size <ONDISK_BUFFER_SIZE>'\n");
+                return 2;
+            }
         } else if (a == "--device") {
             device = atoi(value("--device"));
         } else if (a == "--timing") {
@@ -166,6 +174,7 @@ int main(int argc, char **argv) {
         yb_destroy(ctx);
         return 1;
     };
+    if (ondisk) yb_set_chunk_intervals(ctx, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(ondisk_buffer_size / 8, 1024), 0xFFFFFFFFull));
     const double t1 = now_s();
     const bool from_report = yb_file_type(input.c_str()) == 'y';  // main.rs:43-45
     if ((from_report ? yb_init_report(ctx, input.c_str()) : yb_init_file(ctx, input.c_str())) != YB_OK) return fail("reading the input");

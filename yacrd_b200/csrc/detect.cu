@@ -49,6 +49,24 @@ constexpr uint32_t INF = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// The same decision, with the double-precision division (a long instruction sequence) only where single precision
+// cannot tell: f = bad / len in float is within 2^-20 relative of the exact quotient, so outside that band around
+// not_cov the comparison is already decided. NaN / infinity on either side compare false twice and take the exact path.
+struct NotCovBand {
+    float lo, hi;
+};
+__device__ __forceinline__ NotCovBand not_cov_band(double not_cov) {
+    const float f = (float)not_cov, w = fabsf(f) * 4e-6f + 1e-30f;
+    return {f - w, f + w};
+}
+__device__ __forceinline__ uint32_t classify(uint32_t bad_len, uint32_t len, uint32_t n_up, double not_cov);
+__device__ __forceinline__ uint32_t classify_fast(uint32_t bad_len, uint32_t len, uint32_t n_up, double not_cov, NotCovBand band) {
+    const float f = __fdividef((float)bad_len, (float)len);
+    if (f > band.hi) return 2u;
+    if (f < band.lo) return n_up >= 2u ? 1u : 0u;
+    return classify(bad_len, len, n_up, not_cov);
+}
+
 __device__ __forceinline__ uint32_t classify(uint32_t bad_len, uint32_t len, uint32_t n_up, double not_cov) {
     // editor/mod.rs:88: `bad_region_len as f64 / length as f64 > not_covered` (NaN compares false)
     const double ratio = (double)bad_len / (double)len;
@@ -91,7 +109,12 @@ constexpr uint32_t kScatterRows = 1024;        // rows per CTA of scatter_kernel
 #define YB_ORDER_ROWS 4
 #endif
 constexpr uint32_t kOrderThreads = YB_ORDER_THREADS, kOrderRows = YB_ORDER_ROWS, kPartRows = kOrderThreads * kOrderRows;  // rows per CTA of order_kernel
-static_assert(kOrderRows == 1 || kOrderRows == 2 || kOrderRows == 4, "order_kernel: 1, 2 or 4 rows per thread");
+static_assert(kOrderRows == 4, "order_kernel: a thread's 4 rows travel as one 16-byte word");
+#ifndef YB_ORDER_UNROLL
+#define YB_ORDER_UNROLL 4
+#endif
+constexpr uint32_t kOrderUnroll = YB_ORDER_UNROLL;
+constexpr uint32_t kOrderMap = 1024;  // regions of a warp's 128 rows whose row is looked up in the warp's byte map  // regions a thread moves per turn (loads in flight)
 constexpr uint32_t kStageChunk = 2048;       // pairs a warp reserves in the staging buffer per atomic (an L2 round trip the warp waits for)
 constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
 
@@ -843,11 +866,13 @@ __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long lon
 }
 
 #ifndef YB_ORDER_MIN_CTAS
-#define YB_ORDER_MIN_CTAS (1024 / YB_ORDER_THREADS)
+#define YB_ORDER_MIN_CTAS 6
 #endif
 __global__ void __launch_bounds__(kOrderThreads, YB_ORDER_MIN_CTAS) order_kernel(DetectArgs a, Work w, double not_cov) {
     constexpr uint32_t R = kOrderRows, NW = kOrderThreads / 32;
     __shared__ uint32_t s_warp[NW], s_pre[NW], s_hist[NW], s_last, s_part;
+    __shared__ __align__(16) uint32_t s_off[kPartRows], s_src[kPartRows], s_len[kPartRows], s_bad[kPartRows];
+    __shared__ __align__(16) uint8_t s_int[kPartRows], s_map[NW][kOrderMap];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
@@ -870,24 +895,19 @@ __global__ void __launch_bounds__(kOrderThreads, YB_ORDER_MIN_CTAS) order_kernel
     }
     __syncthreads();
     const uint32_t part = s_part, r0 = part * kPartRows + tid * R;
-    // everything the rows need is requested up front; the first two regions of a row (most have <= 3) ride along
     uint2 m[R];
     uint32_t l[R];
     const bool full = r0 + R <= a.n_reads;
     if (full) {
         const uint4 *mp = reinterpret_cast<const uint4 *>(w.meta + r0);
-        const uint4 *lp = reinterpret_cast<const uint4 *>(a.len + r0);
 #pragma unroll
         for (uint32_t i = 0; i < R / 2; ++i) {
             const uint4 x = mp[i];
             m[2 * i] = make_uint2(x.x, x.y);
             m[2 * i + 1] = make_uint2(x.z, x.w);
         }
-#pragma unroll
-        for (uint32_t i = 0; i < R / 4; ++i) {
-            const uint4 x = __ldg(lp + i);
-            l[4 * i] = x.x, l[4 * i + 1] = x.y, l[4 * i + 2] = x.z, l[4 * i + 3] = x.w;
-        }
+        const uint4 x = __ldg(reinterpret_cast<const uint4 *>(a.len + r0));
+        l[0] = x.x, l[1] = x.y, l[2] = x.z, l[3] = x.w;
     } else {
 #pragma unroll
         for (uint32_t i = 0; i < R; ++i) {
@@ -896,26 +916,33 @@ __global__ void __launch_bounds__(kOrderThreads, YB_ORDER_MIN_CTAS) order_kernel
             l[i] = live ? __ldg(a.len + r0 + i) : 0u;
         }
     }
-    uint2 v0[R], v1[R];
-#pragma unroll
-    for (uint32_t i = 0; i < R; ++i) {
-        v0[i] = v1[i] = make_uint2(0u, 0u);
-        if (m[i].y > 0u) v0[i] = w.stage[m[i].x];
-        if (m[i].y > 1u) v1[i] = w.stage[m[i].x + 1u];
-    }
     uint32_t mine = 0;
 #pragma unroll
     for (uint32_t i = 0; i < R; ++i) mine += m[i].y;
     const uint32_t incl = warp_incl_scan(mine);
     if (lane == 31u) s_warp[wid] = incl;
+    {  // the rows' places in the part, for the threads that will move their regions
+        uint32_t o = incl - mine;  // within the warp; the warps before this one are added by the reader (s_wbase)
+        *reinterpret_cast<uint4 *>(s_src + tid * R) = make_uint4(m[0].x, m[1].x, m[2].x, m[3].x);
+        *reinterpret_cast<uint4 *>(s_len + tid * R) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4 *>(s_bad + tid * R) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint32_t *>(s_int + tid * R) = 0u;
+        uint4 oo;
+        oo.x = o, o += m[0].y;
+        oo.y = o, o += m[1].y;
+        oo.z = o, o += m[2].y;
+        oo.w = o;
+        *reinterpret_cast<uint4 *>(s_off + tid * R) = oo;
+    }
     __syncthreads();
     const unsigned long long tag = (unsigned long long)(ep + 1u) << 32;
-    if (tid == 0) {  // the part's total, for the parts behind this one
-        uint32_t tot = 0;
+    uint32_t wbase = 0, tot = 0;  // regions of the warps before this one, of the part
 #pragma unroll
-        for (uint32_t q = 0; q < NW; ++q) tot += s_warp[q];
-        st_desc(w.part_desc + part, tag | tot);
+    for (uint32_t q = 0; q < NW; ++q) {
+        wbase += q < wid ? s_warp[q] : 0u;
+        tot += s_warp[q];
     }
+    if (tid == 0) st_desc(w.part_desc + part, tag | tot);  // the part's total, for the parts behind this one
     uint32_t pre = 0;  // totals of the parts before this one (they hold earlier tickets: running or done)
     for (uint32_t i0 = tid; i0 < part; i0 += 8u * kOrderThreads) {  // eight loads in flight per thread, the stragglers polled
         unsigned long long d[8];
@@ -930,43 +957,100 @@ __global__ void __launch_bounds__(kOrderThreads, YB_ORDER_MIN_CTAS) order_kernel
     pre = __reduce_add_sync(FULL, pre);
     if (lane == 0u) s_pre[wid] = pre;
     __syncthreads();
-    uint32_t gp = incl - mine;
+    uint32_t gp0 = 0;  // where the part's regions start in the output
 #pragma unroll
-    for (uint32_t q = 0; q < NW; ++q) gp += s_pre[q] + (q < wid ? s_warp[q] : 0u);
-    if (tid == kOrderThreads - 1u && part == w.n_parts - 1u) a.gap_ptr[a.n_reads] = gp + mine;
+    for (uint32_t q = 0; q < NW; ++q) gp0 += s_pre[q];
+    if (tid == kOrderThreads - 1u && part == w.n_parts - 1u) a.gap_ptr[a.n_reads] = gp0 + tot;
+    // The regions move from the staging buffer to their final place warp by warp (a warp owns 128 consecutive rows and so
+    // a contiguous stretch of the output): one region per lane and turn, consecutive lanes writing consecutive regions
+    // whatever row they belong to, every load of a turn in flight together. (A thread walking its own rows' regions
+    // waits a DRAM latency per region of its longest row with the rest of its warp idle.) The row of a region comes
+    // from a byte map the warp fills first (row owners write their rows' entries: two stores for most rows), or, when
+    // the warp's rows have more regions than the map holds, from a bisection over the rows' offsets.
+    {
+        const uint32_t wrow = wid * 32u * R, wtot = s_warp[wid], gpw = gp0 + wbase;
+        const uint32_t *so = s_off + wrow, *ssrc = s_src + wrow, *slen = s_len + wrow;
+        uint32_t *sbad = s_bad + wrow;
+        uint8_t *sint = s_int + wrow, *mp = s_map[wid];
+        const bool mapped = wtot <= kOrderMap;
+        if (mapped) {
+            uint32_t o = incl - mine, longrows = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < R; ++i) {
+                const uint32_t n = m[i].y, rl = lane * R + i;
+                if (n > 0u) mp[o] = (uint8_t)rl;
+                if (n > 1u) mp[o + 1u] = (uint8_t)rl;
+                if (n > 2u) {
+                    if (n <= 34u) {
+                        for (uint32_t gq = 2; gq < n; ++gq) mp[o + gq] = (uint8_t)rl;
+                    } else {
+                        longrows |= 1u << i;
+                    }
+                }
+                o += n;
+            }
+            if (__any_sync(FULL, longrows != 0u)) {  // rows with many regions: the whole warp fills their entries
+                uint32_t oo = incl - mine;
+#pragma unroll
+                for (uint32_t i = 0; i < R; ++i) {
+                    uint32_t todo = __ballot_sync(FULL, (longrows >> i) & 1u);
+                    while (todo) {
+                        const uint32_t sl = __ffs(todo) - 1u;
+                        todo &= todo - 1u;
+                        const uint32_t ob = __shfl_sync(FULL, oo, sl), nb = __shfl_sync(FULL, m[i].y, sl);
+                        for (uint32_t gq = 2u + lane; gq < nb; gq += 32u) mp[ob + gq] = (uint8_t)(sl * R + i);
+                    }
+                    oo += m[i].y;
+                }
+            }
+            __syncwarp();
+        }
+        for (uint32_t e0 = lane; e0 < wtot; e0 += kOrderUnroll * 32u) {
+            uint32_t row[kOrderUnroll];
+            uint2 v[kOrderUnroll];
+#pragma unroll
+            for (uint32_t u = 0; u < kOrderUnroll; ++u) {
+                const uint32_t e = e0 + u * 32u;
+                row[u] = 0;
+                if (e < wtot) {
+                    uint32_t lo = 0;
+                    if (mapped) {
+                        lo = mp[e];
+                    } else {  // last row whose offset is <= e
+#pragma unroll
+                        for (uint32_t h = 16u * R; h > 0u; h >>= 1)
+                            if (so[lo + h] <= e) lo += h;
+                    }
+                    row[u] = lo;
+                    v[u] = w.stage[ssrc[lo] + (e - so[lo])];
+                }
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < kOrderUnroll; ++u) {
+                const uint32_t e = e0 + u * 32u;
+                if (e < wtot) {
+                    a.gaps[gpw + e] = v[u];
+                    atomicAdd(sbad + row[u], v[u].y - v[u].x);
+                    if (v[u].x != 0u && v[u].y != slen[row[u]]) sint[row[u]] = 1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    uint32_t gp = gp0 + wbase + incl - mine;
+    const NotCovBand band = not_cov_band(not_cov);
     uint32_t off[R], cl[R], h1 = 0, h2 = 0, bits = 0;
 #pragma unroll
     for (uint32_t i = 0; i < R; ++i) {
         off[i] = gp;
-        const uint32_t n = m[i].y;
-        uint32_t bad = 0, interior = 0;
-        if (n > 0u) {
-            a.gaps[gp] = v0[i];
-            bad += v0[i].y - v0[i].x;
-            interior |= (v0[i].x != 0u && v0[i].y != l[i]) ? 1u : 0u;
-        }
-        if (n > 1u) {
-            a.gaps[gp + 1u] = v1[i];
-            bad += v1[i].y - v1[i].x;
-            interior |= (v1[i].x != 0u && v1[i].y != l[i]) ? 1u : 0u;
-        }
-        for (uint32_t gq = 2; gq < n; ++gq) {
-            const uint2 v = w.stage[m[i].x + gq];
-            a.gaps[gp + gq] = v;
-            bad += v.y - v.x;
-            interior |= (v.x != 0u && v.y != l[i]) ? 1u : 0u;
-        }
-        gp += n;
-        cl[i] = r0 + i < a.n_reads ? classify(bad, l[i], interior ? 2u : 0u, not_cov) : 0u;
+        gp += m[i].y;
+        cl[i] = r0 + i < a.n_reads ? classify_fast(s_bad[tid * R + i], l[i], s_int[tid * R + i] ? 2u : 0u, not_cov, band) : 0u;
         h1 += cl[i] == 1u;
         h2 += cl[i] == 2u;
         bits |= cl[i] << (2u * i);
     }
     if (full) {
-        uint4 *gpp = reinterpret_cast<uint4 *>(a.gap_ptr + r0);
-#pragma unroll
-        for (uint32_t i = 0; i < R / 4; ++i) gpp[i] = make_uint4(off[4 * i], off[4 * i + 1], off[4 * i + 2], off[4 * i + 3]);
-        static_assert(R == 4, "class codes of a thread's rows go out as one 4-byte store");
+        *reinterpret_cast<uint4 *>(a.gap_ptr + r0) = make_uint4(off[0], off[1], off[2], off[3]);
         *reinterpret_cast<uint32_t *>(a.cls + r0) = cl[0] | cl[1] << 8 | cl[2] << 16 | cl[3] << 24;
     } else {
 #pragma unroll
@@ -1004,7 +1088,7 @@ __global__ void __launch_bounds__(kOrderThreads, YB_ORDER_MIN_CTAS) order_kernel
         if (n_live - c1 - c2) atomicAdd(slot + 0, n_live - c1 - c2);
         if (c1) atomicAdd(slot + 1, c1);
         if (c2) atomicAdd(slot + 2, c2);
-        __threadfence();
+        if (a.n_peers) __threadfence();
         s_last = atomicAdd(cnt + kCntDone, 1u) == w.n_parts - 1u;
     }
     __syncthreads();
@@ -1329,6 +1413,40 @@ const DevCfg *dev_cfg() {
 }
 
 }  // namespace
+
+// The same statistics from the host copy of the row pointers (their differences only: a chunk's pointers need not start
+// at 0). The streamed path uses it: a chunk's upload then has no device round trip in it, and the H2D engine no bubble.
+void host_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out) {
+    *out = DevRowStats{};
+    int cls_of_slabs[kRegisterTierMaxK / kE + 1];  // class_of_row by ceil(k / kE), for the rows of the register tier
+    for (uint32_t q = 0; q <= kRegisterTierMaxK / kE; ++q) cls_of_slabs[q] = class_of_row(q * kE, 0);
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        const uint32_t p0 = rowptr[r], p1 = rowptr[r + 1], l = len[r];
+        if (l > kMaxLength) ++out->bad_len;
+        if (p1 < p0) {
+            ++out->bad_rowptr;
+            continue;
+        }
+        const uint32_t k = p1 - p0;
+        const int cls = k > kRegisterTierMaxK ? -1 : cls_of_slabs[(k + kE - 1) / kE] + (l > kPackedMaxLen ? kNumG : 0);
+        if (cls < 0) {
+            ++out->n_big;
+            out->big_pairs += (unsigned long long)k + 1ull;
+            if (big_row_scans(k, l)) {
+                ++out->n_scan;
+                out->max_len_scan = std::max(out->max_len_scan, l);
+            } else {
+                out->max_k_sort = std::max(out->max_k_sort, k);
+                const unsigned long long hk = cta_words(k, l > kPackedMaxLen);
+                if (hk > kCtaMaxSmemWords) out->huge_keys += hk;
+            }
+        } else {
+            ++out->class_count[cls];
+        }
+        if (l > kPackedMaxLen) ++out->n_wide;
+        out->max_k = std::max(out->max_k, k);
+    }
+}
 
 int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream) {
     if (cudaMemsetAsync(out, 0, sizeof(DevRowStats), stream) != cudaSuccess) return -1;

@@ -55,6 +55,18 @@ struct PinnedBuf {  // page-locked host buffer, grown geometrically (plain memor
         cap = want;
         return true;
     }
+    bool grow_keep(size_t n, size_t used) {  // like reserve, but the first `used` elements survive
+        if (n <= cap) return true;
+        PinnedBuf<T> bigger;
+        bigger.plain = plain;
+        if (!bigger.reserve(n + n / 4)) return false;
+        if (used) memcpy(bigger.p, p, used * sizeof(T));
+        release();
+        p = bigger.p;
+        cap = bigger.cap;
+        bigger.p = nullptr;
+        return true;
+    }
     void release() {
         if (p) {
             if (plain) free(p);
@@ -123,6 +135,14 @@ struct yb_ctx {
     PinnedBuf<uint32_t> h_valid;
     uint32_t n_literal = 0, n_malformed = 0;
     bool bulk_frozen = false;  // the CSR came straight from the parallel ingester: `pending` does not hold it
+    // Streamed batches (yb_set_chunk_intervals): the host CSR goes through the device in row chunks of about this many
+    // intervals, on two lanes (child contexts with their own streams and device buffers), so that chunk k + 1 crosses
+    // PCIe while chunk k is computed and chunk k - 1's results come back.
+    uint32_t chunk_intervals = 0;
+    std::vector<yb_ctx *> lanes;
+    bool is_lane = false;
+    uint32_t rowptr_base = 0;  // lane: the chunk's first row pointer (subtracted on the device)
+    uint32_t n_chunks_last = 0;
     std::string error;
 
     // ---- host store (Reads2Ovl producer side) ----
@@ -246,9 +266,9 @@ int freeze(yb_ctx *c) {
     if (c->frozen) return YB_OK;
     if (c->b_rowptr) {  // borrowed CSR: nothing to build; the rows are inspected on the device at upload
         const uint32_t n = c->n_indexed;
-        if (n && c->b_rowptr[0] != 0) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr[0] must be 0");
+        if (n && c->b_rowptr[0] != c->rowptr_base) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr[0] must be 0");
         c->n_reads = n;
-        c->n_iv = n ? c->b_rowptr[n] : 0;
+        c->n_iv = n ? c->b_rowptr[n] - c->rowptr_base : 0;
         c->frozen = true;
         return YB_OK;
     }
@@ -385,6 +405,8 @@ yb_ctx *yb_create(const yb_opts *opts) {
 
 void yb_destroy(yb_ctx *c) {
     if (!c) return;
+    for (yb_ctx *l : c->lanes) yb_destroy(l);
+    c->lanes.clear();
     if (c->host_only) {
         c->h_rowptr.release();
         c->h_len.release();
@@ -800,6 +822,12 @@ static int detect_args(yb_ctx *c, yb::DetectArgs *out) {
 }
 
 // ---- staged device API -------------------------------------------------------------------------------
+// A lane's row pointers arrive as they are in the caller's CSR; the chunk's first one is subtracted in place.
+__global__ void __launch_bounds__(256) rebase_kernel(uint32_t *rowptr, uint32_t n, uint32_t base) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n) rowptr[i] -= base;
+}
+
 int yb_upload(yb_ctx *c) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
     if (c->host_only) return c->fail(YB_ERR_CUDA, "host-only context: the detect path runs on a CUDA device only");
@@ -817,20 +845,31 @@ int yb_upload(yb_ctx *c) {
     if (n) {
         YB_CUDA(c, cudaMemcpyAsync(c->d_rowptr.p, c->rowptr_host(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, c->stream));
         YB_CUDA(c, cudaMemcpyAsync(c->d_len.p, c->len_host(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        if (c->rowptr_base) {
+            rebase_kernel<<<(unsigned)((n + 256) / 256), 256, 0, c->stream>>>(c->d_rowptr.p, (uint32_t)n + 1u, c->rowptr_base);
+            c->stats.kernel_launches += 1;
+        }
     }
-    // size classes, big-row scratch needs and input sanity come from one small kernel over rowptr / len; its
-    // 128-byte result crosses PCIe while the interval buffer is still on its way
-    const int sl = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->stream);
-    if (sl < 0) return c->cuda_fail(cudaGetLastError(), "row statistics kernel");
-    c->stats.kernel_launches += (uint64_t)sl;
-    YB_CUDA(c, cudaMemcpyAsync(c->h_rowstats.p, c->d_rowstats.p, sizeof(yb::DevRowStats), cudaMemcpyDeviceToHost, c->stream));
-    cudaEvent_t ev;
-    YB_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    YB_CUDA(c, cudaEventRecord(ev, c->stream));
-    if (n && m) YB_CUDA(c, cudaMemcpyAsync(c->d_iv.p, c->iv_host(), sizeof(uint2) * m, cudaMemcpyHostToDevice, c->stream));
-    const cudaError_t ee = cudaEventSynchronize(ev);
-    cudaEventDestroy(ev);
-    if (ee != cudaSuccess) return c->cuda_fail(ee, "cudaEventSynchronize");
+    if (c->is_lane) {
+        // a chunk of a streamed run: the statistics come from the host copy (the host thread is ahead of the transfers
+        // anyway), so nothing below waits for the device and the H2D engine goes from one chunk straight to the next
+        if (n && m) YB_CUDA(c, cudaMemcpyAsync(c->d_iv.p, c->iv_host(), sizeof(uint2) * m, cudaMemcpyHostToDevice, c->stream));
+        yb::host_row_stats(c->rowptr_host(), c->len_host(), c->n_reads, c->h_rowstats.p);  // (while the chunk crosses PCIe)
+    } else {
+        // size classes, big-row scratch needs and input sanity come from one small kernel over rowptr / len; its
+        // 128-byte result crosses PCIe while the interval buffer is still on its way
+        const int sl = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->stream);
+        if (sl < 0) return c->cuda_fail(cudaGetLastError(), "row statistics kernel");
+        c->stats.kernel_launches += (uint64_t)sl;
+        YB_CUDA(c, cudaMemcpyAsync(c->h_rowstats.p, c->d_rowstats.p, sizeof(yb::DevRowStats), cudaMemcpyDeviceToHost, c->stream));
+        cudaEvent_t ev;
+        YB_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        YB_CUDA(c, cudaEventRecord(ev, c->stream));
+        if (n && m) YB_CUDA(c, cudaMemcpyAsync(c->d_iv.p, c->iv_host(), sizeof(uint2) * m, cudaMemcpyHostToDevice, c->stream));
+        const cudaError_t ee = cudaEventSynchronize(ev);
+        cudaEventDestroy(ev);
+        if (ee != cudaSuccess) return c->cuda_fail(ee, "cudaEventSynchronize");
+    }
     {
         const yb::DevRowStats &ds = *c->h_rowstats.p;
         if (ds.bad_rowptr) return c->fail(YB_ERR_INVALID_ARGUMENT, "rowptr is not monotone (%u reads)", ds.bad_rowptr);
@@ -960,6 +999,42 @@ int yb_time_upload_kernels(yb_ctx *c, float *ms_out) {
     return rc;
 }
 
+int yb_time_one_shot(yb_ctx *c, uint64_t coverage, double not_coverage, float *ms_upload_kernels, float *ms_first_step) {
+    if (!c || !ms_upload_kernels || !ms_first_step) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->uploaded || c->from_report) return c->fail(YB_ERR_STATE, "yb_time_one_shot needs an uploaded CSR");
+    YB_DEVICE(c);
+    YB_CUDA(c, cudaSetDevice(c->device));
+    cudaEvent_t e0, e1, e2;
+    YB_CUDA(c, cudaEventCreate(&e0));
+    YB_CUDA(c, cudaEventCreate(&e1));
+    YB_CUDA(c, cudaEventCreate(&e2));
+    c->validated = c->valid_pending = false;  // as after yb_upload: the step below tests every interval
+    c->n_literal = c->n_malformed = 0;
+    yb::DetectArgs a{};
+    int rc = detect_args(c, &a);
+    if (rc == YB_OK) {
+        cudaEventRecord(e0, c->stream);
+        const int l0 = yb::launch_row_stats(c->d_rowptr.p, c->d_len.p, c->n_reads, c->d_rowstats.p, c->stream);
+        const int l1 = yb::launch_upload_kernels(a, c->stream);
+        cudaEventRecord(e1, c->stream);
+        const int l2 = yb::launch_detect(a, coverage > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)coverage, not_coverage, c->stream);
+        cudaEventRecord(e2, c->stream);
+        if (l0 < 0 || l1 < 0 || l2 < 0 || cudaEventSynchronize(e2) != cudaSuccess || cudaEventElapsedTime(ms_upload_kernels, e0, e1) != cudaSuccess ||
+            cudaEventElapsedTime(ms_first_step, e1, e2) != cudaSuccess)
+            rc = c->cuda_fail(cudaGetLastError(), "one-shot timing");
+        else
+            c->stats.kernel_launches += (uint64_t)(l0 + l1 + l2);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    c->coverage = coverage;
+    c->not_coverage = not_coverage;
+    c->computed = rc == YB_OK;
+    c->downloaded = false;
+    return rc;
+}
+
 int yb_peer_wait(yb_ctx *c, void *stream) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
     if (!c->n_peers) return YB_OK;
@@ -982,8 +1057,9 @@ int yb_synchronize(yb_ctx *c) {
     return YB_OK;
 }
 
-int yb_download(yb_ctx *c) {
-    if (!c) return YB_ERR_INVALID_ARGUMENT;
+// The results of c's last step go to dst's host arrays: dst == c (row0 = gap0 = 0) for a whole CSR; for a lane of a
+// streamed run dst is the parent, row0 the chunk's first read and gap0 the bad regions of the chunks before it.
+static int download_impl(yb_ctx *c, yb_ctx *dst, size_t row0, size_t gap0) {
     if (!c->computed) return c->fail(YB_ERR_STATE, "yb_download before yb_compute_device");
     if (c->downloaded) return YB_OK;
     YB_DEVICE(c);
@@ -994,21 +1070,23 @@ int yb_download(yb_ctx *c) {
     }
     const size_t n = c->n_reads;
     const bool peers = c->n_peers && !c->from_report;
-    if (!c->h_cls.reserve(n + 1) || !c->h_gap_ptr.reserve(n + 1) || !c->h_bitmap.reserve(2 * (c->bitmap_bytes() + 4)) ||
+    if ((dst == c && (!c->h_cls.reserve(n + 1) || !c->h_gap_ptr.reserve(n + 1) || !c->h_bitmap.reserve(2 * (c->bitmap_bytes() + 4)))) ||
         !c->h_counters.reserve(yb::kCounterWords) || !c->h_peer_step.reserve(1))
         return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
+    uint32_t *const gap_ptr_dst = dst->h_gap_ptr.p + row0;
+    uint8_t *const bitmap_dst = dst->h_bitmap.p + row0 / 4;  // (a chunk starts at a multiple of 1024 reads)
     YB_CUDA(c, cudaMemcpyAsync(c->h_counters.p, c->d_counters.p, sizeof(uint32_t) * yb::kCounterWords, cudaMemcpyDeviceToHost, c->stream));
-    YB_CUDA(c, cudaMemcpyAsync(c->h_gap_ptr.p, c->d_gap_ptr.p, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, c->stream));
+    YB_CUDA(c, cudaMemcpyAsync(gap_ptr_dst, c->d_gap_ptr.p, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, c->stream));
     const size_t bmb = c->bitmap_bytes();
     if (n) {
-        YB_CUDA(c, cudaMemcpyAsync(c->h_cls.p, c->d_cls.p, n, cudaMemcpyDeviceToHost, c->stream));
+        YB_CUDA(c, cudaMemcpyAsync(dst->h_cls.p + row0, c->d_cls.p, n, cudaMemcpyDeviceToHost, c->stream));
         if (peers) {  // this rank's slot of the last step: even steps use the first half of the gather buffer, odd ones the second
             const uint8_t *own = c->peer_gather[c->peer_rank] + (size_t)c->peer_rank * c->peer_slot_bytes;
             YB_CUDA(c, cudaMemcpyAsync(c->h_peer_step.p, c->peer_flags[c->peer_rank] + 31, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p, own, bmb, cudaMemcpyDeviceToHost, c->stream));
             YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p + bmb + 4, own + (size_t)c->n_peers * c->peer_slot_bytes, bmb, cudaMemcpyDeviceToHost, c->stream));
         } else {
-            YB_CUDA(c, cudaMemcpyAsync(c->h_bitmap.p, c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p, bmb, cudaMemcpyDeviceToHost, c->stream));
+            YB_CUDA(c, cudaMemcpyAsync(bitmap_dst, c->ext_bitmap ? c->ext_bitmap : c->d_bitmap.p, bmb, cudaMemcpyDeviceToHost, c->stream));
         }
     }
     YB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1024,13 +1102,18 @@ int yb_download(yb_ctx *c) {
     if (hc[yb::kCntOrderTimeout]) return c->fail(YB_ERR_STATE, "internal error: the ordering kernel did not complete");
     if (set[yb::kCntStageOverflow])
         return c->fail(YB_ERR_STATE, "internal error: bad-region staging buffer overflow (%u reads)", set[yb::kCntStageOverflow]);
-    c->n_gaps = c->h_gap_ptr.p[n];
+    c->n_gaps = gap_ptr_dst[n];
     size_t d2h = sizeof(uint32_t) * (n + 1 + yb::kCounterWords) + n + bmb;
     if (!c->from_report) {
-        if (!c->h_gaps.reserve((size_t)c->n_gaps + 1)) return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
+        if (!(dst == c ? c->h_gaps.reserve((size_t)c->n_gaps + 1) : dst->h_gaps.grow_keep(gap0 + c->n_gaps + 1, gap0)))
+            return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
         if (c->n_gaps) {
-            YB_CUDA(c, cudaMemcpyAsync(c->h_gaps.p, c->d_gaps.p, sizeof(uint2) * c->n_gaps, cudaMemcpyDeviceToHost, c->stream));
+            YB_CUDA(c, cudaMemcpyAsync(dst->h_gaps.p + gap0, c->d_gaps.p, sizeof(uint2) * c->n_gaps, cudaMemcpyDeviceToHost, c->stream));
+            if (gap0)  // (while the regions cross PCIe)
+                for (size_t i = 0; i <= n; ++i) gap_ptr_dst[i] += (uint32_t)gap0;
             YB_CUDA(c, cudaStreamSynchronize(c->stream));
+        } else if (gap0) {
+            for (size_t i = 0; i <= n; ++i) gap_ptr_dst[i] += (uint32_t)gap0;
         }
         d2h += sizeof(uint2) * c->n_gaps;
     }
@@ -1060,8 +1143,117 @@ int yb_download(yb_ctx *c) {
     return YB_OK;
 }
 
+int yb_download(yb_ctx *c) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    return download_impl(c, c, 0, 0);
+}
+
+int yb_set_chunk_intervals(yb_ctx *c, uint32_t n_intervals) {
+    if (!c) return YB_ERR_INVALID_ARGUMENT;
+    c->chunk_intervals = n_intervals;
+    return YB_OK;
+}
+
+// Streamed yb_compute_all_bad_part: row chunks of about chunk_intervals intervals alternate between two lanes. The
+// host thread only ever blocks for the chunk two behind the one it just enqueued, so the H2D engine always has the
+// next chunk queued (PCIe is what bounds the whole call: 8 bytes per interval in, about 0.5 out), the kernels of a
+// chunk run under the next chunk's transfer, and the results land directly in this context's host arrays.
+static int compute_streamed(yb_ctx *c, uint64_t coverage, double not_coverage) {
+    const uint32_t n = c->n_reads;
+    const uint32_t *rp = c->rowptr_host();
+    if (!c->h_cls.reserve((size_t)n + 1) || !c->h_gap_ptr.reserve((size_t)n + 1) || !c->h_bitmap.reserve(2 * (c->bitmap_bytes() + 4)))
+        return c->fail(YB_ERR_NOMEM, "pinned host allocation failed");
+    while (c->lanes.size() < 2) {
+        yb_opts o{};
+        o.device = c->device;
+        o.read_buffer_size = c->read_buffer_size;
+        o.flags = c->flags & ~(uint32_t)(YB_FLAG_HOST_ONLY | YB_FLAG_LAZY_DEVICE);
+        yb_ctx *l = yb_create(&o);
+        if (!l) return c->fail(YB_ERR_CUDA, "streamed batches: %s", yb_create_error());
+        l->is_lane = true;
+        c->lanes.push_back(l);
+    }
+    struct InFlight {
+        bool busy = false;
+        uint32_t row0 = 0;
+    } fl[2];
+    size_t gap0 = 0;
+    yb_stats tot{};
+    uint32_t n_chunks = 0;
+    auto finish = [&](int li) -> int {
+        yb_ctx *l = c->lanes[li];
+        if (int rc = download_impl(l, c, fl[li].row0, gap0)) return c->fail(rc, "%s", l->error.c_str());
+        gap0 += l->n_gaps;
+        if (gap0 > 0xFFFFFFF0ull) return c->fail(YB_ERR_TOO_LARGE, "more than 2^32-16 bad regions");
+        tot.n_not_bad += l->stats.n_not_bad;
+        tot.n_chimeric += l->stats.n_chimeric;
+        tot.n_not_covered += l->stats.n_not_covered;
+        tot.n_malformed_intervals += l->stats.n_malformed_intervals;
+        tot.n_literal_reads += l->stats.n_literal_reads;
+        tot.max_intervals_per_read = std::max(tot.max_intervals_per_read, l->stats.max_intervals_per_read);
+        tot.h2d_bytes += l->stats.h2d_bytes;
+        tot.d2h_bytes += l->stats.d2h_bytes;
+        tot.kernel_launches += l->stats.kernel_launches;
+        fl[li].busy = false;
+        return YB_OK;
+    };
+    uint32_t r0 = 0;
+    int li = 0;
+    while (r0 < n) {
+        // the chunk ends at the first multiple of 1024 reads that holds chunk_intervals intervals (or at the end)
+        const uint32_t *stop = std::lower_bound(rp + r0 + 1, rp + n, rp[r0] + c->chunk_intervals);
+        uint32_t r1 = (uint32_t)(stop - rp);
+        r1 = (uint32_t)std::min<uint64_t>(n, ((uint64_t)r1 + 1023u) & ~(uint64_t)1023u);
+        if (fl[li].busy)
+            if (int rc = finish(li)) return rc;
+        yb_ctx *l = c->lanes[li];
+        if (int rc = yb_reset(l)) return rc;
+        l->stats = yb_stats{};
+        l->rowptr_base = rp[r0];
+        if (int rc = yb_bind_csr(l, rp + r0, reinterpret_cast<const uint32_t *>(c->iv_host() + rp[r0]), c->len_host() + r0, r1 - r0))
+            return c->fail(rc, "%s", l->error.c_str());
+        if (int rc = yb_upload(l)) return c->fail(rc, "%s", l->error.c_str());
+        if (int rc = yb_compute_device(l, coverage, not_coverage, nullptr)) return c->fail(rc, "%s", l->error.c_str());
+        fl[li].busy = true;
+        fl[li].row0 = r0;
+        ++n_chunks;
+        r0 = r1;
+        li ^= 1;
+    }
+    for (int k = 0; k < 2; ++k, li ^= 1)  // the older chunk first: its regions come first
+        if (fl[li].busy)
+            if (int rc = finish(li)) return rc;
+    c->n_gaps = (uint32_t)gap0;
+    c->h_gap_ptr.p[n] = (uint32_t)gap0;
+    c->max_k = tot.max_intervals_per_read;
+    c->stats.n_reads = n;
+    c->stats.n_intervals = c->n_iv;
+    c->stats.n_gaps = gap0;
+    c->stats.n_not_bad = tot.n_not_bad;
+    c->stats.n_chimeric = tot.n_chimeric;
+    c->stats.n_not_covered = tot.n_not_covered;
+    c->stats.n_malformed_intervals = tot.n_malformed_intervals;
+    c->stats.n_literal_reads = tot.n_literal_reads;
+    c->stats.max_intervals_per_read = tot.max_intervals_per_read;
+    c->stats.h2d_bytes += tot.h2d_bytes;
+    c->stats.d2h_bytes += tot.d2h_bytes;
+    c->stats.kernel_launches += tot.kernel_launches;
+    c->n_chunks_last = n_chunks;
+    c->coverage = coverage;
+    c->not_coverage = not_coverage;
+    c->computed = c->downloaded = true;
+    return YB_OK;
+}
+
+
 int yb_compute_all_bad_part(yb_ctx *c, uint64_t coverage, double not_coverage) {
     if (!c) return YB_ERR_INVALID_ARGUMENT;
+    if (!c->from_report && c->chunk_intervals && !c->host_only && !c->n_peers && !c->ext_bitmap && !c->uploaded) {
+        YB_DEVICE(c);
+        YB_CUDA(c, cudaSetDevice(c->device));
+        if (int rc = freeze(c)) return rc;
+        if (c->n_iv > c->chunk_intervals) return compute_streamed(c, coverage, not_coverage);
+    }
     if (!c->from_report)
         if (int rc = yb_upload(c)) return rc;
     if (int rc = yb_compute_device(c, coverage, not_coverage, nullptr)) return rc;

@@ -155,6 +155,8 @@ struct DevRowStats {
 };
 // Zeroes *out and fills it from the device-resident rowptr / len (one kernel on `stream`). Returns launches or -1.
 int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream);
+// The same from host arrays (only differences of the row pointers are used), for the streamed path.
+void host_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out);
 
 // Once per uploaded CSR (it depends on rowptr / len only, not on the threshold - the reference builds its read index, a
 // hash map, while it ingests): scatter_kernel, the size-class worklist of the register tier (16 bytes per read: row,
