@@ -145,7 +145,9 @@ class Arm:
         self.name, self.rank, self.world, self.dev, self.stream, self.args = name, rank, world, dev, stream, args
         self.n_glob, mean, profile, self.c, self.nn, self.desc = WORKLOADS[name]
         t0 = time.perf_counter()
-        self.csr = yb.synth_csr(self.n_glob, mean, profile=profile, seed=SEED, shard=rank, n_shards=world)
+        # --shard-of N (development aid, one GPU): time shard 0 of an N-way split, i.e. what one rank of an N-GPU run computes
+        n_shards = args.shard_of if (world == 1 and args.shard_of > 1) else world
+        self.csr = yb.synth_csr(self.n_glob, mean, profile=profile, seed=SEED, shard=rank, n_shards=n_shards)
         self.t_gen = time.perf_counter() - t0
         self.fm = yb.FullMemory(device=local_rank)
         self.fm.bind_csr(self.csr)
@@ -367,8 +369,9 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the short measurements of the other BASELINE configs")
     ap.add_argument("--nccl-allgather", action="store_true", help="N > 1: NCCL all-gather instead of the peer-memory epilogue")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph per step")
-    ap.add_argument("--chunk-intervals", type=int, default=8_000_000,
-                    help="e2e arm: streamed batches of about this many intervals (64 MB, the reference's --ondisk-buffer-size default); 0 = one shot")
+    ap.add_argument("--shard-of", type=int, default=0, help="development aid (one GPU): run shard 0 of an N-way split; `value` is then meaningless")
+    ap.add_argument("--chunk-intervals", type=int, default=16_000_000,
+                    help="e2e arm: streamed batches of about this many intervals (128 MB of intervals); 0 = one shot")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

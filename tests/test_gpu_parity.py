@@ -322,6 +322,27 @@ def test_config5_like_skewed_pacbio():
     assert_same_as_oracle(csr.rowptr, csr.iv, csr.length, 3, 0.4)
 
 
+def test_config5_full_size_500k_reads():
+    """BASELINE config 5 at full size (500 k reads, PacBio Sequel lengths, Pareto k capped at 5000, -c 3 -n 0.4): every
+    tier runs (register tier, position scan, CTA sort). Full comparison with the oracle, one shot and streamed."""
+    csr = yb.synth_csr(500_000, 0, profile=yb.SYNTH_PACBIO_SKEW)
+    w_cls, w_gp, w_gaps = o.run_csr(csr.rowptr, csr.iv, csr.length, 3, 0.4)
+    fm = yb.FullMemory()
+    for chunk in (0, 3_000_000):
+        fm.reset()
+        fm.set_chunk_intervals(chunk)
+        fm.bind_csr(csr)
+        bp = yb.FromOverlap(fm, 3, 0.4)
+        bp.compute_all_bad_part()
+        gp, gaps = bp.gap_csr()
+        assert np.array_equal(gp.astype(np.uint64), w_gp) and np.array_equal(gaps, w_gaps) and np.array_equal(bp.classes(), w_cls)
+        assert np.array_equal(ybd.unpack_bitmap(bp.class_bitmap(), len(w_cls)), w_cls)
+        st = fm.stats()
+        assert st["max_intervals_per_read"] > 2048 and st["n_gaps"] == len(w_gaps)
+    fm.close()
+    csr.free()
+
+
 def test_config3_full_size_2m_reads():
     """BASELINE config 3 at full size (2 M reads x mean 50, -c 4 -n 0.4): full comparison with the oracle
     (multi-threaded C) plus size-independent properties."""

@@ -115,6 +115,10 @@ static_assert(kOrderRows == 4, "order_kernel: a thread's 4 rows travel as one 16
 #endif
 constexpr uint32_t kOrderUnroll = YB_ORDER_UNROLL;
 constexpr uint32_t kOrderMap = 1024;  // regions of a warp's 128 rows whose row is looked up in the warp's byte map  // regions a thread moves per turn (loads in flight)
+#ifndef YB_STATIC_EIGHTHS
+#define YB_STATIC_EIGHTHS 0
+#endif
+constexpr uint32_t kStaticEighths = YB_STATIC_EIGHTHS;  // share of sort_kernel's batches dealt round-robin (the rest dynamically)
 constexpr uint32_t kStageChunk = 2048;       // pairs a warp reserves in the staging buffer per atomic (an L2 round trip the warp waits for)
 constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
 
@@ -764,6 +768,11 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_next;
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
+#ifdef YB_TRACE_CTA
+    unsigned long long tr_t0, tr_t1 = 0, tr_t2;
+    uint32_t tr_n = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0));
+#endif
     WarpSmem &ws = *reinterpret_cast<WarpSmem *>(smem_raw + wid * kWarpSmemBytes);
     uint2 *buf = reinterpret_cast<uint2 *>(smem_raw + wid * kWarpSmemBytes + sizeof(WarpSmem));
     if (lane == 0) {
@@ -778,23 +787,34 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
     ClassCursor cu;
     cu.q = 0;
     cursor_load(tab, cu);
-#ifdef YB_STATIC_SCHED
-    uint32_t local_next = wid;
-    auto draw_raw = [&]() {  // fixed deal inside the CTA as well: warp w takes the CTA's batches w, w + WARPS, ...
-        const uint32_t t = local_next;
-        local_next += kSortWarps;
-        return t;
-    };
-#else
-    auto draw_raw = [&]() {  // the CTA's next batch (lane 0 holds it; indices drawn by a warp only grow)
+    // Batches are dealt in two ways. The first kStaticEighths / 8 of them round-robin over the CTAs (CTA b takes b, b + grid,
+    // ...; inside a CTA a shared-memory counter hands them to the warps): no global traffic, but SMs do not all run at
+    // the same speed (a few per cent, measured), so a fixed deal leaves the slowest CTA working alone at the end. The
+    // rest, the cheap classes of the end of the processing order, from a global cursor: CTAs that are ahead take more.
+    // The global cursor is a double: ptxas turns an integer atomicAdd of one lane into its warp-aggregated form, whose
+    // shuffle needs the result at once, i.e. a stall of an L2 round trip per batch; the f64 add (ATOMG.E.ADD.F64) is left
+    // alone, and its result is only needed a batch later.
+    const uint32_t quota = (uint32_t)((uint64_t)n_items * kStaticEighths / 8u / gridDim.x), n_static = quota * gridDim.x;
+    double *dyn_cursor = reinterpret_cast<double *>(cnt + kCntDynTicket);
+    bool dyn = quota == 0u;
+    auto draw_raw = [&]() {  // the warp's next batch (lane 0 holds it; indices drawn by a warp only grow)
         uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(&s_next, 1u);
+        if (lane == 0) {
+            if (!dyn) {
+                t = atomicAdd(&s_next, 1u);
+                dyn = t >= quota;
+                t = t * gridDim.x + blockIdx.x;
+            }
+            if (dyn) {
+                const double d = atomicAdd(dyn_cursor, 1.0);
+                t = d < 4.0e9 ? n_static + __double2uint_rz(d) : 0xFFFFFFFFu;
+            }
+        }
         return t;
     };
-#endif
-    auto draw_done = [&](uint32_t raw) {  // (called a batch after draw_raw: the shared-memory atomic has long returned)
-        const uint64_t it = (uint64_t)__shfl_sync(FULL, raw, 0) * gridDim.x + blockIdx.x;
-        return it < n_items ? (uint32_t)it : n_items;
+    auto draw_done = [&](uint32_t raw) {  // (called a batch after draw_raw: the atomic has long returned)
+        const uint32_t it = __shfl_sync(FULL, raw, 0);
+        return it < n_items ? it : n_items;
     };
     uint32_t item = draw_done(draw_raw()), item1 = draw_done(draw_raw()), item2 = draw_done(draw_raw());
     // software pipeline: the record of batch i+2 is on its way to shared memory, the slab copies of batch i+1 are issued
@@ -830,6 +850,9 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
         }
 #undef YB_CASE
         __syncwarp();
+#ifdef YB_TRACE_CTA
+        if (tr_n++ == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t1));
+#endif
         rec0 = ws.rec[s][lane];
         cls0 = cls1;
         cls1 = cls2;
@@ -840,6 +863,12 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
         s ^= 1u;
         parity ^= 1u;
     }
+#ifdef YB_TRACE_CTA
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t2));
+    if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 73 || blockIdx.x == 147))
+        printf("TRACE val=%d cta %u warp %u t0 %llu first %llu end %llu batches %u\n", (int)VAL, blockIdx.x, wid, tr_t0, tr_t1 ? tr_t1 - tr_t0 : 0ull,
+               tr_t2 - tr_t0, tr_n);
+#endif
 }
 
 constexpr size_t kSortSmemBytes = kWarpSmemBytes * kSortWarps;

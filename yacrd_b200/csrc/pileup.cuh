@@ -28,6 +28,7 @@ enum Counter : uint32_t {
     kCntPeerTimeout = 15,  // a peer never signalled the previous step (a rank died or never launched)
     kCntDone = 16,       // order_kernel: parts finished (the last one closes the step)
     kCntLiteral = 17,    // cursor over the list of malformed rows (literal heap sweep)
+    kCntDynTicket = 18,  // (two words, a double) sort_kernel: cursor over the dynamically dealt batches
     kCntHist = 32,       // kHistSlots x {NotBad, Chimeric, NotCovered}: the detect step's class histogram, striped
     kNumCounters = 32 + 3 * 32
 };
