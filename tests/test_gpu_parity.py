@@ -171,6 +171,21 @@ def test_corrupt_report_is_an_error():
     assert e.value.kind == "CorruptYacrdReport"
 
 
+def test_failed_report_load_leaves_an_empty_usable_context():
+    fm = yb.FullMemory()
+    bad = b"NotBad\tgood\t100\t\nNotCovered\tbroken\t30116\t326,0,326;27159,2957\n"
+    assert fm._L.yb_init_report_buffer(fm._h, bad, len(bad)) == -7
+    assert fm.n_reads() == 0 and fm.length("good") == 0
+    huge = b"NotBad\tr\t4294967296\t\n"  # the classifier holds lengths in 32 bits
+    assert fm._L.yb_init_report_buffer(fm._h, huge, len(huge)) == -11
+    assert fm.n_reads() == 0
+    fm.add_overlap_and_length("good", (10, 90), 100)  # the same context takes a detect batch afterwards
+    bp = yb.FromOverlap(fm, 0)
+    bp.compute_all_bad_part()
+    assert bp.get_bad_part("good") == ([(0, 10), (90, 100)], 100)
+    fm.close()
+
+
 def test_malformed_intervals_follow_the_reference_kats():
     """begin >= end or end > length: the reference has no such test and its heap sweep gives a definite answer
     (stack.rs:61-139); those reads take literal_kernel. One read each, against the oracle's literal sweep."""

@@ -8,10 +8,12 @@ from yacrd_b200 import _native as N
 
 n_rec = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
 n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else n_rec // 25
+import workload
 L = N.lib()
-need = L.yb_synth_paf(20261017, n_reads, n_rec, None, 0)
+W = workload.lib()
+need = W.yb_synth_paf(20261017, n_reads, n_rec, None, 0)
 buf = np.empty(need, dtype=np.uint8)
-nb = L.yb_synth_paf(20261017, n_reads, n_rec, buf.ctypes.data, need)
+nb = W.yb_synth_paf(20261017, n_reads, n_rec, buf.ctypes.data, need)
 path = "/tmp/yb_synth_%d.paf" % n_rec
 buf[:nb].tofile(path)
 del buf

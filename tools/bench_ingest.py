@@ -10,11 +10,13 @@ from yacrd_b200 import _native as N
 n_rec = int(sys.argv[1]) if len(sys.argv) > 1 else 5_000_000
 n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else max(1000, n_rec // 25)
 threads = [int(x) for x in sys.argv[3:]] or [1, 2, 4, 8, 0]
+import workload
 L = N.lib()
-need = L.yb_synth_paf(20261017, n_reads, n_rec, None, 0)
+W = workload.lib()
+need = W.yb_synth_paf(20261017, n_reads, n_rec, None, 0)
 buf = np.empty(need, dtype=np.uint8)
 t0 = time.perf_counter()
-nb = L.yb_synth_paf(20261017, n_reads, n_rec, buf.ctypes.data, need)
+nb = W.yb_synth_paf(20261017, n_reads, n_rec, buf.ctypes.data, need)
 print("synthetic PAF: %d records, %d reads, %.1f MB (generated in %.2f s), %d cores" % (n_rec, n_reads, nb / 1e6, time.perf_counter() - t0, os.cpu_count()))
 ref = None
 for th in threads:

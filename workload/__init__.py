@@ -1,6 +1,7 @@
-"""Synthetic workloads of BASELINE.json's configs without the product library: numpy buffers
-filled by workload/libyacrd_synth.so (workload/synth.cpp, the same generator the product library exports as yb_synth_*).
-Used by bench.py --impl reference, whose process must not map libyacrd_b200.so."""
+"""Synthetic workloads of BASELINE.json's configs: workload/libyacrd_synth.so (workload/synth.cpp,
+declarations in workload/synth.h), measurement and test infrastructure that is not part of the product library. Both
+bench arms and the tests generate their inputs here; `synth_csr` fills plain numpy buffers (the reference arm's process
+never maps libyacrd_b200.so), yacrd_b200.synth_csr fills a page-locked PinnedCsr through the same entry points."""
 import ctypes as C
 import os
 import subprocess
@@ -35,6 +36,10 @@ def lib():
         L.yb_synth_plan.argtypes = [C.POINTER(SynthSpec), C.c_void_p, C.c_void_p, C.c_void_p]
         L.yb_synth_fill.restype = C.c_int
         L.yb_synth_fill.argtypes = [C.POINTER(SynthSpec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+        L.yb_synth_shard_of.restype = C.c_uint32
+        L.yb_synth_shard_of.argtypes = [C.c_uint32, C.c_uint32]
+        L.yb_synth_paf.restype = C.c_uint64
+        L.yb_synth_paf.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 

@@ -1,7 +1,6 @@
 // synth.cpp — synthetic overlap workloads for BASELINE.json's configs. Host only, no CUDA.
-// Compiled twice: into the product library (the yb_synth_* entries of include/yacrd_b200.h) and, by workload/Makefile,
-// into workload/libyacrd_synth.so, which bench.py's reference arm and the oracle-side tools load instead, so that the
-// CPU arm never maps the product library.
+// Built by workload/Makefile into workload/libyacrd_synth.so (declarations: workload/synth.h): measurement and test
+// infrastructure, not part of the product library. Both bench arms and the tests load it from there.
 //
 // Counter-based: every value of read r is a pure function of (seed, r), so a shard can be generated
 // on its own and any subset of reads reproduces bit for bit. Reads are assigned to shards by
@@ -26,7 +25,7 @@
 #include <thread>
 #include <vector>
 
-#include "../include/yacrd_b200.h"
+#include "synth.h"
 
 namespace {
 
@@ -163,7 +162,7 @@ uint64_t yb_synth_plan(const yb_synth_spec *sp, uint32_t *global_idx, uint32_t *
 
 int yb_synth_fill(const yb_synth_spec *sp, const uint32_t *global_idx, const uint32_t *rowptr, const uint32_t *length,
                   uint32_t n_local, uint32_t *iv, int threads) {
-    if (!sp || !rowptr || !length || !iv) return YB_ERR_INVALID_ARGUMENT;
+    if (!sp || !rowptr || !length || !iv) return -9;  // (invalid argument)
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     threads = (int)std::min<uint32_t>((uint32_t)threads, std::max(1u, n_local));
     auto work = [&](uint32_t r0, uint32_t r1) {
@@ -181,7 +180,7 @@ int yb_synth_fill(const yb_synth_spec *sp, const uint32_t *global_idx, const uin
         if (r > r0) pool.emplace_back(work, r0, r);
     }
     for (auto &th : pool) th.join();
-    return YB_OK;
+    return 0;
 }
 
 // Synthetic PAF text for the ingestion bench: n_records overlap records between pseudo-random pairs of

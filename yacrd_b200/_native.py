@@ -93,9 +93,6 @@ SIGNATURES = {
     "yb_device_gap_ptr": (_vp, [_vp, C.POINTER(_sz)]),
     "yb_device_gaps": (_vp, [_vp, C.POINTER(_sz)]),
     "yb_get_stats": (C.c_int, [_vp, C.POINTER(YbStats)]),
-    "yb_synth_shard_of": (C.c_uint32, [C.c_uint32, C.c_uint32]),
-    "yb_synth_count": (C.c_uint32, [C.POINTER(YbSynthSpec)]),
-    "yb_synth_plan": (C.c_uint64, [C.POINTER(YbSynthSpec), _vp, _vp, _vp]),
     "yb_peer_alloc": (_vp, [_vp, _sz, _vp]),
     "yb_peer_open": (_vp, [_vp, _vp]),
     "yb_peer_close": (C.c_int, [_vp, _vp]),
@@ -105,8 +102,6 @@ SIGNATURES = {
     "yb_time_upload_kernels": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "yb_set_chunk_intervals": (C.c_int, [_vp, C.c_uint32]),
     "yb_time_one_shot": (C.c_int, [_vp, C.c_uint64, C.c_double, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
-    "yb_synth_paf": (C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint64, _vp, C.c_uint64]),
-    "yb_synth_fill": (C.c_int, [C.POINTER(YbSynthSpec), _vp, _vp, _vp, C.c_uint32, _vp, C.c_int]),
 }
 
 _lib = None

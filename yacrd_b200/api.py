@@ -15,6 +15,7 @@ Every call that computes goes through libyacrd_b200.so (sm_100a kernels); nothin
 from __future__ import annotations
 
 import ctypes as C
+import os
 import enum
 
 import numpy as np
@@ -186,14 +187,26 @@ class PinnedCsr:
             pass
 
 
+def _workload():
+    """The synthetic workload generator lives outside the product library (workload/libyacrd_synth.so)."""
+    try:
+        import workload
+    except ImportError:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import workload
+    return workload
+
+
 def synth_shard_of(read, n_shards):
-    return N.lib().yb_synth_shard_of(int(read), int(n_shards))
+    return _workload().lib().yb_synth_shard_of(int(read), int(n_shards))
 
 
 def synth_csr(n_reads, mean_intervals, profile=N.SYNTH_ONT, seed=20261017, shard=0, n_shards=1, threads=0):
     """Synthetic workload for one shard, as a PinnedCsr (global_idx filled in)."""
-    L = N.lib()
-    spec = N.YbSynthSpec(seed, n_reads, shard, n_shards, profile, float(mean_intervals))
+    W = _workload()
+    L = W.lib()
+    spec = W.SynthSpec(seed, n_reads, shard, n_shards, profile, float(mean_intervals))
     n_local = L.yb_synth_count(C.byref(spec))
     gidx = np.zeros(max(1, n_local), dtype=np.uint32)
     rowptr = np.zeros(n_local + 1, dtype=np.uint32)
@@ -207,8 +220,8 @@ def synth_csr(n_reads, mean_intervals, profile=N.SYNTH_ONT, seed=20261017, shard
     csr.global_idx = gidx[:n_local]
     rc = L.yb_synth_fill(C.byref(spec), gidx.ctypes.data, csr.rowptr.ctypes.data, csr.length.ctypes.data,
                          n_local, csr.iv.ctypes.data if tot else None, threads)
-    if rc != N.OK:
-        raise N.YacrdError(rc, "yb_synth_fill")
+    if rc != 0:
+        raise RuntimeError("yb_synth_fill failed (%d)" % rc)
     return csr
 
 

@@ -619,6 +619,7 @@ static bool add_sink(void *sink, const char *id, size_t id_len, uint32_t b, uint
 
 static bool alloc_csr_sink(void *sink, size_t n_reads, size_t n_iv, uint32_t **rowptr, uint32_t **len, uint32_t **iv) {
     yb_ctx *c = static_cast<yb_ctx *>(sink);
+    if (!c->host_only && c->device >= 0) cudaSetDevice(c->device);  // (lazy context: page-lock on its device, not on device 0)
     if (!c->h_rowptr.reserve(n_reads + 1) || !c->h_len.reserve(n_reads + 1) || !c->h_iv.reserve(n_iv + 1)) return false;
     *rowptr = c->h_rowptr.p;
     *len = c->h_len.p;
@@ -888,6 +889,14 @@ int yb_upload(yb_ctx *c) {
     }
     // once per CSR (it cannot change afterwards): the size-class worklist of the register tier. The intervals themselves
     // are tested by the first detect step.
+    // the device counts staged regions, offsets and worklist entries in 32 bits: refuse what could wrap them
+    // (1.5 (n_iv + n_reads) + 2 n_reads staged pairs + one open chunk per resident warp, detect.cu:carve)
+    {
+        const uint64_t s = (uint64_t)c->n_iv + c->n_reads;
+        if (s + s / 2 + 2ull * c->n_reads + 4096ull * 2048ull > 0xFFFFFFF0ull)
+            return c->fail(YB_ERR_TOO_LARGE, "batch too large for one context (%u reads, %u intervals): split it (yb_set_chunk_intervals)",
+                           c->n_reads, c->n_iv);
+    }
     const size_t sb = yb::detect_scratch_bytes(c->n_reads, c->n_iv, c->rows);
     if (!c->d_scratch.reserve(sb)) return c->fail(YB_ERR_NOMEM, "device scratch allocation failed (%zu bytes)", sb);
     {
@@ -1495,8 +1504,18 @@ int yb_write_report(yb_ctx *c, const char *path) {  // main.rs:62-84
 }
 
 // ---- FromReport (stack.rs:176-257) -------------------------------------------------------------------
+static int init_report_impl(yb_ctx *c, const char *text, size_t n_bytes);
 int yb_init_report_buffer(yb_ctx *c, const char *text, size_t n_bytes) {
     if (!c || (!text && n_bytes)) return YB_ERR_INVALID_ARGUMENT;
+    const int rc = init_report_impl(c, text, n_bytes);
+    if (rc != YB_OK && rc != YB_ERR_STATE) {  // a failed load leaves an empty context, not a half-filled one
+        const std::string why = c->error;
+        yb_reset(c);
+        c->error = why;
+    }
+    return rc;
+}
+static int init_report_impl(yb_ctx *c, const char *text, size_t n_bytes) {
     if (c->host_only) return c->fail(YB_ERR_CUDA, "host-only context: reports are classified on a CUDA device only");
     if (c->total_reads() || c->from_report) return c->fail(YB_ERR_STATE, "yb_init_report needs an empty context");
     YB_DEVICE(c);
@@ -1544,6 +1563,8 @@ int yb_init_report_buffer(yb_ctx *c, const char *text, size_t n_bytes) {
         while (bad_e < le && *bad_e != '\t') ++bad_e;
         uint64_t len;
         if (!parse_u(len_s, len_e, UINT64_MAX, &len)) return corrupt(line);
+        if (len > 0xFFFFFFFFull)  // the classifier holds lengths in 32 bits; the reference divides by the full usize
+            return c->fail(YB_ERR_TOO_LARGE, "line %llu: read length %llu does not fit 32 bits", (unsigned long long)line, (unsigned long long)len);
         bool is_new;
         const uint32_t idx = c->ids.intern(id, (size_t)(id_e - id), &is_new);
         const uint32_t g0 = (uint32_t)gaps.size();

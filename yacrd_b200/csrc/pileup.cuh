@@ -19,8 +19,6 @@ enum Counter : uint32_t {
     kCntChimeric = 1,
     kCntNotCovered = 2,
     kCntMalformed = 3,   // intervals violating 0 <= begin < end <= length seen by the CTA tier
-    kCntTile = 4,        // dynamic batch scheduler of sort_kernel (packed rows)
-    kCntTileWide = 5,    // the same for the long reads' kernel
     kCntHugeBump = 6,    // bump allocator (in u32 keys) of the global-scratch tier
     kCntStage = 11,      // bump allocator (in pairs) of the bad-region staging buffer
     kCntTicket = 13,     // order_kernel: dynamic part index (a part only waits for parts that already run)
@@ -150,9 +148,7 @@ struct DevRowStats {
     uint32_t pad_;
     unsigned long long big_pairs;  // sum over big rows of k + 1
     unsigned long long huge_keys;  // sum over rows beyond the shared-memory tier of next_pow2(2k)
-    uint32_t malformed;            // intervals violating 0 <= begin < end <= length (launch_validate)
-    uint32_t malformed_rows;       // rows holding at least one of them (they take the literal heap sweep)
-    uint32_t pad2_[2];
+    uint32_t pad2_[4];
 };
 // Zeroes *out and fills it from the device-resident rowptr / len (one kernel on `stream`). Returns launches or -1.
 int launch_row_stats(const uint32_t *rowptr, const uint32_t *len, uint32_t n_reads, DevRowStats *out, cudaStream_t stream);

@@ -185,9 +185,6 @@ __device__ __forceinline__ uint32_t atom_add_u32(uint32_t *p, uint32_t v) {
     asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
     return r;
 }
-__device__ __forceinline__ void red_add_u32(uint32_t *p, uint32_t v) {
-    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 __device__ __forceinline__ uint32_t top_bits(uint32_t n) { return n >= 32u ? FULL : ~(FULL >> n); }  // the n most significant bits
 
