@@ -812,10 +812,8 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
         }
         return t;
     };
-    auto draw_done = [&](uint32_t raw) {  // (called a batch after draw_raw: the atomic has long returned)
-        const uint32_t it = __shfl_sync(FULL, raw, 0);
-        return it < n_items ? it : n_items;
-    };
+    auto clamp_item = [&](uint32_t it) { return it < n_items ? it : n_items; };
+    auto draw_done = [&](uint32_t raw) { return clamp_item(__shfl_sync(FULL, raw, 0)); };
     uint32_t item = draw_done(draw_raw()), item1 = draw_done(draw_raw()), item2 = draw_done(draw_raw());
     // software pipeline: the record of batch i+2 is on its way to shared memory, the slab copies of batch i+1 are issued
     // as soon as the keys of batch i are in registers (one slab buffer) and land while batch i is sorted
@@ -830,6 +828,12 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
     uint2 chunk = make_uint2(0, 0);  // [next free pair, end) of the warp's staging chunk
     while (item < n_items) {
         const uint32_t raw3 = draw_raw();  // consumed at the end of this iteration
+        // the loop's state goes to shared memory for the time the batch is sorted and comes back after (see WarpSmem::st)
+        if (lane == 0) {
+            ws.st[0] = item1, ws.st[1] = item2, ws.st[2] = cls1, ws.st[3] = cls2, ws.st[4] = s, ws.st[5] = parity;
+            ws.st[6] = cu.q, ws.st[7] = cu.lo, ws.st[8] = cu.hi, ws.st[9] = cu.cls, ws.st[10] = cu.G, ws.st[11] = cu.rpb;
+            ws.st[12] = cu.inv, ws.st[13] = cu.ebase, ws.st[14] = cu.count;
+        }
         mbar_wait(&ws.mbar, parity);
         fetch_wait();  // (issued a batch ago)
         auto refill = [&]() {
@@ -837,6 +841,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (item1 < n_items) issue_batch(a, buf, &ws.mbar, ws.rec[s][lane], ws.geo[s][lane], lane);
+            if (lane == 0) ws.st[15] = raw3;  // (the keys are in registers: the draw's L2 round trip is over, or nearly)
         };
 #define YB_CASE(gi)                                                                                                        \
     case gi: process_batch_t<class_lanes_c(gi), true, VAL>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;        \
@@ -853,12 +858,12 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
 #ifdef YB_TRACE_CTA
         if (tr_n++ == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t1));
 #endif
+        s = ws.st[4];
         rec0 = ws.rec[s][lane];
-        cls0 = cls1;
-        cls1 = cls2;
-        item = item1;
-        item1 = item2;
-        item2 = draw_done(raw3);
+        item = ws.st[0], item1 = ws.st[1], cls0 = ws.st[2], cls1 = ws.st[3], parity = ws.st[5];
+        cu.q = ws.st[6], cu.lo = ws.st[7], cu.hi = ws.st[8], cu.cls = ws.st[9], cu.G = ws.st[10], cu.rpb = ws.st[11];
+        cu.inv = ws.st[12], cu.ebase = ws.st[13], cu.count = ws.st[14];
+        item2 = clamp_item(ws.st[15]);
         fetch_rec(w, tab, cu, ws.rec[s], ws.geo[s], item2, n_items, cls2, lane);
         s ^= 1u;
         parity ^= 1u;

@@ -173,6 +173,8 @@ struct alignas(16) WarpSmem {  // one per warp: a warp runs on its own, no CTA-w
     unsigned long long pad_;
     uint4 rec[2][32];  // worklist records of the next two batches, one per lane (cp.async)
     uint32_t geo[2][32];  // and the lanes' places in those batches (fetch_rec)
+    uint32_t st[16];      // the batch loop's own state while a batch is sorted (sort_kernel: every register is needed there,
+                          // and what ptxas spills to local memory comes back from L2, ~270 cycles a piece)
     uint32_t scr[kScrWords2];
 };
 static_assert(sizeof(WarpSmem) % 16 == 0, "the slab must stay 16-byte aligned");
