@@ -115,10 +115,6 @@ static_assert(kOrderRows == 4, "order_kernel: a thread's 4 rows travel as one 16
 #endif
 constexpr uint32_t kOrderUnroll = YB_ORDER_UNROLL;
 constexpr uint32_t kOrderMap = 1024;  // regions of a warp's 128 rows whose row is looked up in the warp's byte map  // regions a thread moves per turn (loads in flight)
-#ifndef YB_STATIC_EIGHTHS
-#define YB_STATIC_EIGHTHS 0
-#endif
-constexpr uint32_t kStaticEighths = YB_STATIC_EIGHTHS;  // share of sort_kernel's batches dealt round-robin (the rest dynamically)
 constexpr uint32_t kStageChunk = 2048;       // pairs a warp reserves in the staging buffer per atomic (an L2 round trip the warp waits for)
 constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
 
@@ -766,7 +762,6 @@ __device__ __forceinline__ void issue_batch(const DetectArgs &a, uint2 *buf, uns
 template <bool VAL>
 __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Work w, ClassTab tab, uint32_t c, PipeMul pm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint32_t s_next;
     const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
 #ifdef YB_TRACE_CTA
     unsigned long long tr_t0, tr_t1 = 0, tr_t2;
@@ -779,7 +774,6 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
         mbar_init(&ws.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x == 0) s_next = 0u;
     __syncthreads();
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
@@ -787,33 +781,19 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
     ClassCursor cu;
     cu.q = 0;
     cursor_load(tab, cu);
-    // Batches are dealt in two ways. The first kStaticEighths / 8 of them round-robin over the CTAs (CTA b takes b, b + grid,
-    // ...; inside a CTA a shared-memory counter hands them to the warps): no global traffic, but SMs do not all run at
-    // the same speed (a few per cent, measured), so a fixed deal leaves the slowest CTA working alone at the end. The
-    // rest, the cheap classes of the end of the processing order, from a global cursor: CTAs that are ahead take more.
-    // The global cursor is a double: ptxas turns an integer atomicAdd of one lane into its warp-aggregated form, whose
-    // shuffle needs the result at once, i.e. a stall of an L2 round trip per batch; the f64 add (ATOMG.E.ADD.F64) is left
-    // alone, and its result is only needed a batch later.
-    const uint32_t quota = (uint32_t)((uint64_t)n_items * kStaticEighths / 8u / gridDim.x), n_static = quota * gridDim.x;
+    // Batches are dealt from one global cursor, in processing order: SMs do not all run at the same speed (a few per
+    // cent, measured), and a fixed deal leaves the slowest CTA working alone at the end. The cursor is a double: ptxas
+    // turns an integer atomicAdd of one lane into its warp-aggregated form, whose shuffle needs the result at once, i.e. a
+    // stall of an L2 round trip per batch; the f64 add (ATOMG.E.ADD.F64) is left alone, and its result is first touched
+    // when the batch's keys are in registers (refill, below).
     double *dyn_cursor = reinterpret_cast<double *>(cnt + kCntDynTicket);
-    bool dyn = quota == 0u;
     auto draw_raw = [&]() {  // the warp's next batch (lane 0 holds it; indices drawn by a warp only grow)
-        uint32_t t = 0;
-        if (lane == 0) {
-            if (!dyn) {
-                t = atomicAdd(&s_next, 1u);
-                dyn = t >= quota;
-                t = t * gridDim.x + blockIdx.x;
-            }
-            if (dyn) {
-                const double d = atomicAdd(dyn_cursor, 1.0);
-                t = d < 4.0e9 ? n_static + __double2uint_rz(d) : 0xFFFFFFFFu;
-            }
-        }
-        return t;
+        double d = 0.0;
+        if (lane == 0) d = atomicAdd(dyn_cursor, 1.0);
+        return d;
     };
-    auto clamp_item = [&](uint32_t it) { return it < n_items ? it : n_items; };
-    auto draw_done = [&](uint32_t raw) { return clamp_item(__shfl_sync(FULL, raw, 0)); };
+    auto to_item = [&](double d) { return d < (double)n_items ? __double2uint_rz(d) : n_items; };
+    auto draw_done = [&](double raw) { return __shfl_sync(FULL, to_item(raw), 0); };
     uint32_t item = draw_done(draw_raw()), item1 = draw_done(draw_raw()), item2 = draw_done(draw_raw());
     // software pipeline: the record of batch i+2 is on its way to shared memory, the slab copies of batch i+1 are issued
     // as soon as the keys of batch i are in registers (one slab buffer) and land while batch i is sorted
@@ -827,7 +807,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
     uint32_t parity = 0;
     uint2 chunk = make_uint2(0, 0);  // [next free pair, end) of the warp's staging chunk
     while (item < n_items) {
-        const uint32_t raw3 = draw_raw();  // consumed at the end of this iteration
+        const double raw3 = draw_raw();  // first touched in refill, consumed at the end of this iteration
         // the loop's state goes to shared memory for the time the batch is sorted and comes back after (see WarpSmem::st)
         if (lane == 0) {
             ws.st[0] = item1, ws.st[1] = item2, ws.st[2] = cls1, ws.st[3] = cls2, ws.st[4] = s, ws.st[5] = parity;
@@ -841,7 +821,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (item1 < n_items) issue_batch(a, buf, &ws.mbar, ws.rec[s][lane], ws.geo[s][lane], lane);
-            if (lane == 0) ws.st[15] = raw3;  // (the keys are in registers: the draw's L2 round trip is over, or nearly)
+            if (lane == 0) ws.st[15] = to_item(raw3);  // (the keys are in registers: the draw's L2 round trip is over, or nearly)
         };
 #define YB_CASE(gi)                                                                                                        \
     case gi: process_batch_t<class_lanes_c(gi), true, VAL>(a, w, cnt, ws, buf, rec0, c, chunk, pm, lane, refill); break;        \
@@ -863,7 +843,7 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
         item = ws.st[0], item1 = ws.st[1], cls0 = ws.st[2], cls1 = ws.st[3], parity = ws.st[5];
         cu.q = ws.st[6], cu.lo = ws.st[7], cu.hi = ws.st[8], cu.cls = ws.st[9], cu.G = ws.st[10], cu.rpb = ws.st[11];
         cu.inv = ws.st[12], cu.ebase = ws.st[13], cu.count = ws.st[14];
-        item2 = clamp_item(ws.st[15]);
+        item2 = ws.st[15];
         fetch_rec(w, tab, cu, ws.rec[s], ws.geo[s], item2, n_items, cls2, lane);
         s ^= 1u;
         parity ^= 1u;
