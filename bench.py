@@ -111,7 +111,7 @@ def run_reference(args, rank, world):
     sample_reads = n_glob if args.ref_sample <= 0 else min(n_glob, args.ref_sample)
     csr = workload.synth_csr(sample_reads, mean, profile=profile, seed=SEED)
     runner = o.PaddedRunner(csr.rowptr, csr.iv, csr.length)
-    threads = o.max_threads()
+    threads = args.ref_threads if args.ref_threads > 0 else o.max_threads()
     for _ in range(args.warmup):
         runner.run(c, nn, threads)
     t0 = time.perf_counter()
@@ -365,6 +365,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 10)")
     ap.add_argument("--ref-sample", type=int, default=0, help="reference arm / cpu baseline: reads per step (0 = the whole workload)")
+    ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: host threads (0 = all; 1 = the reference's default -t)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short measurements of the other BASELINE configs")
     ap.add_argument("--nccl-allgather", action="store_true", help="N > 1: NCCL all-gather instead of the peer-memory epilogue")

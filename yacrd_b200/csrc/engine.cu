@@ -846,15 +846,15 @@ int yb_upload(yb_ctx *c) {
     if (n) {
         YB_CUDA(c, cudaMemcpyAsync(c->d_rowptr.p, c->rowptr_host(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, c->stream));
         YB_CUDA(c, cudaMemcpyAsync(c->d_len.p, c->len_host(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
-        if (c->rowptr_base) {
-            rebase_kernel<<<(unsigned)((n + 256) / 256), 256, 0, c->stream>>>(c->d_rowptr.p, (uint32_t)n + 1u, c->rowptr_base);
-            c->stats.kernel_launches += 1;
-        }
     }
     if (c->is_lane) {
         // a chunk of a streamed run: the statistics come from the host copy (the host thread is ahead of the transfers
         // anyway), so nothing below waits for the device and the H2D engine goes from one chunk straight to the next
         if (n && m) YB_CUDA(c, cudaMemcpyAsync(c->d_iv.p, c->iv_host(), sizeof(uint2) * m, cudaMemcpyHostToDevice, c->stream));
+        if (n && c->rowptr_base) {  // behind the copies: a kernel between them would hold the H2D engine until an SM is free
+            rebase_kernel<<<(unsigned)((n + 256) / 256), 256, 0, c->stream>>>(c->d_rowptr.p, (uint32_t)n + 1u, c->rowptr_base);
+            c->stats.kernel_launches += 1;
+        }
         yb::host_row_stats(c->rowptr_host(), c->len_host(), c->n_reads, c->h_rowstats.p);  // (while the chunk crosses PCIe)
     } else {
         // size classes, big-row scratch needs and input sanity come from one small kernel over rowptr / len; its
