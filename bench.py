@@ -175,7 +175,7 @@ class Arm:
             self.gathered = torch.zeros(world, self.slot, dtype=torch.uint8, device=dev)
             self.fm.bind_device_bitmap(self.gathered[rank].data_ptr(), self.slot)
         self.flush = None
-        if self.csr.nbytes < 2 * L2_BYTES:  # shard smaller than ~2x L2: flush L2 between timed iterations
+        if self.csr.nbytes < 1.5 * L2_BYTES:  # shard not clearly larger than L2 (126 MB): flush L2 between timed iterations
             self.flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
         self.graph = None
         self.launches_per_step = None

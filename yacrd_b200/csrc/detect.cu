@@ -1085,7 +1085,8 @@ __global__ void __launch_bounds__(kOrderThreads, YB_ORDER_MIN_CTAS) order_kernel
                   // two slots per rank, alternating with the step, so a reader of step s never sees stores of step s + 1
             const size_t po = (size_t)(peer_step & 1u) * a.peer_parity_bytes;
             for (uint32_t p = 0; p < a.n_peers; ++p) reinterpret_cast<uint32_t *>(a.peer_slot[p] + po)[r0 >> 4] = word;
-            __threadfence_system();
+            // (made visible system-wide by ONE fence of thread 0 behind the CTA barrier below, the grid-sync pattern:
+            // a fence per storing thread kept every CTA alive for 64 NVLink round trips)
         }
     }
     // class histogram: one RED per class per CTA, spread over kHistSlots copies (same-address atomics serialise in L2)
@@ -1102,7 +1103,7 @@ __global__ void __launch_bounds__(kOrderThreads, YB_ORDER_MIN_CTAS) order_kernel
         if (n_live - c1 - c2) atomicAdd(slot + 0, n_live - c1 - c2);
         if (c1) atomicAdd(slot + 1, c1);
         if (c2) atomicAdd(slot + 2, c2);
-        if (a.n_peers) __threadfence();
+        if (a.n_peers) __threadfence_system();  // the CTA's peer stores (ordered before this thread by the barrier) before kCntDone
         s_last = atomicAdd(cnt + kCntDone, 1u) == w.n_parts - 1u;
     }
     __syncthreads();
@@ -1121,7 +1122,7 @@ __global__ void __launch_bounds__(kOrderThreads, YB_ORDER_MIN_CTAS) order_kernel
             }
         }
         if (a.n_peers) {
-            __threadfence_system();  // every part's peer stores (fenced by their writers before kCntDone) before the flags
+            __threadfence_system();  // every part's peer stores (fenced by its thread 0 before kCntDone) before the flags
             if (tid < a.n_peers) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flag[tid] + a.rank), "r"(peer_step + 1u) : "memory");
             if (tid == 0) a.peer_flag[a.rank][31] = peer_step + 1u;
         }
