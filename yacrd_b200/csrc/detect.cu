@@ -1,4 +1,4 @@
-// detect.cu — sm_100a kernels of the detect hot path (v5).
+// detect.cu — sm_100a kernels of the detect hot path.
 //
 // Replaces, per read, FromOverlap::compute_bad_part (reference src/stack.rs:61-139) fused with
 // editor::type_of_read (src/editor/mod.rs:85-100). The reference sorts the intervals and sweeps them with
@@ -20,22 +20,28 @@
 //   bad_len = sum(end - begin) in wrapping u32; NotCovered iff (double)bad_len / (double)len > n (same IEEE
 //   divide, tested first); else Chimeric iff some region has begin != 0 && end != len; else NotBad.
 //
-// Kernels (all integer work; no tensor cores — there is no contraction on this path):
-//   scatter_kernel   every row -> its size class (G = 1,2,3,4,5,6,8,10,16,32 lanes x 16 keys; packed or wide) and
-//                    a 16-byte worklist record {row, first interval, k, len}; rows with k > 512 -> big list.
-//   big_kernel       rows with k > 512: one CTA per row; 512-key chunks sorted by warps in registers, larger strides
-//                    in shared memory (packed keys again; a global slab beyond 32768 intervals).
-//   sort_kernel      persistent warps walk the worklist in batches of floor(32 / G) rows of ONE class, so a
-//                    batch fills the warp with equal-sized lane groups. Each row's interval slab is pulled into
-//                    shared memory by its own TMA bulk copy (cp.async.bulk, SASS UBLKCP; double-buffered: the
-//                    copies of batch i+2 are issued when batch i is done). A group sorts its row in registers as
-//                    PACKED u16x2 keys (begin | end << 16) — one VIMNMX.U16x2 moves a begin and an end through
-//                    the same network, so both sorts cost one — or as two u32 arrays when the read is longer
-//                    than 65534 bases. Crossings come from two carry-chain compares per slot against a
-//                    transposed shared-memory copy; the batch's bad regions go to a bump-allocated staging
-//                    segment (one atomic per batch, no waiting between warps).
-//   order_kernel     single pass over the rows: scan of the per-row counts (decoupled look-back over cheap,
-//                    uniform parts), staging -> ordered bad-region CSR, classification, 2-bit bitmap, histogram.
+// Kernels (all integer work; no tensor cores: there is no contraction on this path). DESIGN.md section 3 has the details.
+//   per upload
+//     row_stats_kernel  size-class histogram, big-row scratch needs, input sanity (from rowptr / len only)
+//     scatter_kernel    every row -> its size class (G = 1,2,3,4,5,8,16 lanes x 32 keys; packed or wide) and a 16-byte
+//                       worklist record {row, first interval, k | class, len}; rows with k > 512 -> scan / big lists
+//   per detect step (no memset: the counters alternate between two sets, see pileup.cuh)
+//     sort_kernel<VAL>  one persistent CTA per SM; warps take batches of floor(32 / G) rows of ONE class from a global
+//                       cursor (regtier.cuh): record prefetch by cp.async, one TMA bulk copy per row (UBLKCP) onto the
+//                       warp's mbarrier, keys sorted in registers as PACKED u16x2 (begin | end << 16: one VIMNMX.U16x2
+//                       moves a begin and an end through the same network) or as two u32 arrays when the read is longer
+//                       than 65534 bases, crossings by carry-chain compares against a transposed shared copy, the row's
+//                       position list written to a bump-allocated staging buffer, meta[row] = {first pair, count}.
+//                       VAL (first step after an upload) also tests 0 <= begin < end <= len; rows that fail go to
+//     literal_kernel    the reference's own algorithm (sort + min-heap sweep, stack.rs:61-139), one thread per row
+//     bigscan_kernel    (side stream) rows with 512 < k <= 65534 on reads shorter than 393216: begins / ends counted per
+//                       position in shared memory, occupied positions compacted and scanned; no sort
+//     big_kernel        (side stream) the remaining big rows: bitonic sort in shared memory / global scratch
+//     order_kernel      one pass: parts of 1024 rows in ticket order publish their totals and sum the earlier ones,
+//                       staged regions -> ordered bad-region CSR, classification, 2-bit bitmap (to every peer's gather
+//                       buffer when peers are bound), class histogram; the last part closes the step
+//     peer_wait_kernel  consumer side of the fused all-gather
+//   classify_kernel     FromReport path: type_of_read over given bad regions
 #include "pileup.cuh"
 #include <algorithm>
 #include <cstdlib>

@@ -6,8 +6,8 @@
 
 namespace yb {
 
-// A read with k intervals has 2k events (one begin key 2b+1, one end key 2e per interval); a u32
-// event key needs positions < 2^31, which the engine enforces at upload (YB_ERR_TOO_LARGE).
+// Read lengths (and so positions) stay below 2^31: the wide keys keep their top bit for +inf padding and the carry-chain
+// compares subtract positions in 32 bits. The engine enforces it at upload (YB_ERR_TOO_LARGE).
 constexpr uint32_t kMaxLength = 0x7FFFFFFFu;
 
 // Device counters. The buffer holds TWO sets of kNumCounters words plus a few persistent words behind them: the detect
@@ -138,7 +138,7 @@ struct DetectArgs {
     size_t scratch_bytes;
 };
 
-// Row statistics gathered on the device at upload time (the host never loops over the rows of a bulk CSR).
+// Row statistics gathered on the device at upload time (the host loops over the rows only for the chunks of a streamed run).
 struct DevRowStats {
     uint32_t class_count[kNumClasses];
     uint32_t n_big, n_wide, max_k;

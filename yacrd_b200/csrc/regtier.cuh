@@ -18,8 +18,9 @@
 // the end that is c (+1) ranks below at a warp-uniform offset and push their carries into bit masks (IADD3 + IMAD.X);
 // (4) the handful of crossings U0 D0 U1 D1 ... goes straight to a bump-allocated segment of the staging buffer as the
 // pair list P[q] = (D_{q-1}, U_q) with D_{-1} = 0 and U_{n} = len: the row's bad regions are a sub-range of it, so per row
-// only one 8-byte record {first pair, count} follows (order_kernel does the rest). The slab is dead as soon as the keys are in registers: the copies of the NEXT batch are issued into the
-// same buffer right after the load phase and land while this batch is sorted (one slab + T = 13 KB per warp).
+// only one 8-byte record {first pair, count} follows (order_kernel does the rest). The slab is dead as soon as the keys
+// are in registers: the copies of the NEXT batch are issued into the same buffer right after the load phase and land
+// while this batch is sorted (one slab + T + records + loop state = 14.3 KB per warp).
 #pragma once
 
 constexpr int kLogE = kE == 32 ? 5 : 4;
