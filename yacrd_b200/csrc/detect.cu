@@ -121,6 +121,11 @@ static_assert(kOrderRows == 4, "order_kernel: a thread's 4 rows travel as one 16
 #endif
 constexpr uint32_t kOrderUnroll = YB_ORDER_UNROLL;
 constexpr uint32_t kOrderMap = 1024;  // regions of a warp's 128 rows whose row is looked up in the warp's byte map  // regions a thread moves per turn (loads in flight)
+#ifndef YB_FIXED_ROUNDS
+#define YB_FIXED_ROUNDS 3
+#endif
+constexpr uint32_t kFixedRounds = YB_FIXED_ROUNDS;  // sort_kernel: batches per warp dealt by position (1 or 3), the rest by the cursor
+static_assert(kFixedRounds == 1 || kFixedRounds == 3, "one or three fixed rounds");
 constexpr uint32_t kStageChunk = 2048;       // pairs a warp reserves in the staging buffer per atomic (an L2 round trip the warp waits for)
 constexpr uint32_t kRecValid = 0x80000000u;    // worklist record .z = k | class << 16 | kRecValid
 
@@ -165,8 +170,12 @@ __global__ void __launch_bounds__(kScatterRows) scatter_kernel(DetectArgs a, Wor
         len = __ldg(a.len + r);
         cls = class_of_row(k, len);
         if (cls < 0) {
-            if (big_row_scans(k, len)) w.scan_list[atomicAdd(a.counters + kCntScanList, 1u)] = r;
-            else w.big_list[atomicAdd(a.counters + kCntBigList, 1u)] = r;
+            if (big_row_scans(k, len)) {  // heavy rows (several windows, or many intervals) to the front, the others to the back
+                if (len >= kScanWindow || k >= 2048u) w.scan_list[atomicAdd(a.counters + kCntScanList, 1u)] = r;
+                else w.scan_list[(uint32_t)a.rows.n_scan - 1u - atomicAdd(a.counters + kCntScanListBack, 1u)] = r;
+            } else {
+                w.big_list[atomicAdd(a.counters + kCntBigList, 1u)] = r;
+            }
         }
     }
     const uint32_t peers = __match_any_sync(FULL, cls);
@@ -526,7 +535,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) bigscan_kernel(DetectArgs a, 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t ep = __ldcg(a.counters + kCntEpoch);
     uint32_t *cnt = a.counters + (ep & 1u) * kNumCounters;
-    const uint32_t n_scan = min((uint32_t)a.rows.n_scan, __ldcg(a.counters + kCntScanList));  // (rows redone by literal_kernel are not listed)
+    const uint32_t n_scan = (uint32_t)a.rows.n_scan;  // (scatter_kernel filled the list from both ends: heavy rows first)
+    __shared__ uint32_t s_nextj;
     const uint32_t cc = min(c, 0x7FFFFFF0u);
     for (uint32_t x = tid; x < kScanWindow; x += kScanThreads) cnt_x[x] = 0u;
     occ[tid] = 0u;
@@ -563,10 +573,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) bigscan_kernel(DetectArgs a, 
     };
     fetch_meta(blockIdx.x);
     fetch_ivs(blockIdx.x);
-    for (uint32_t j = blockIdx.x; j < n_scan; j += gridDim.x) {
+    // rows are dealt in list order from a cursor (the first one per CTA by its index): rows cost anything between one
+    // window of 600 intervals and several windows of 5000, and a fixed deal left SMs idle for a fifth of the kernel
+    for (uint32_t j = blockIdx.x, jn = 0; j < n_scan; j = jn) {
         const uint32_t r = r_n, s = s_n, k = k_n, len = len_n;
         const uint32_t n_pos = len + 1u;  // positions 0 .. len
         if (tid == 0) {
+            s_nextj = gridDim.x + atomicAdd(cnt + kCntScanTicket, 1u);
             s_v[2] = atomicAdd(cnt + kCntStage, k + 1u);  // the pair list P[q] = (D_{q-1}, U_q), q = 0 .. n_up <= k
             s_v[3] = 0u;                                  // validating step: the row holds a malformed interval
         }
@@ -575,6 +588,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) bigscan_kernel(DetectArgs a, 
         for (uint32_t lo = 0; lo < n_pos; lo += kScanWindow) {
             const uint32_t m = min(kScanWindow, n_pos - lo);
             __syncthreads();  // the previous window is cleared
+            jn = s_nextj;
             auto count = [&](const uint2 v) {
                 if (a.validate && lo == 0u) nbad += !(v.x < v.y && v.y <= len);
                 const uint32_t xb = v.x - lo, xe = v.y - lo;
@@ -593,7 +607,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) bigscan_kernel(DetectArgs a, 
             for (uint32_t i = tid + NPF * kScanThreads; i < k; i += kScanThreads) count(__ldg(a.iv + s + i));
             if (nbad) s_v[3] = 1u;
             if (lo + kScanWindow >= n_pos) {  // last window: the registers are free for the next row
-                fetch_meta(j + gridDim.x);
+                fetch_meta(jn);
             }
             __syncthreads();
             // compact the occupied positions (ascending), then thread t takes entries [e0, e1)
@@ -638,7 +652,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) bigscan_kernel(DetectArgs a, 
                 walk([&](uint32_t x) { P[2u * ru++ + 1u] = x; }, [&](uint32_t x) { P[2u * rd++ + 2u] = x; });
             }
             for (uint32_t e = e0; e < e1; ++e) cnt_x[lst[e]] = 0u;  // leave the window clean
-            if (lo + kScanWindow >= n_pos) fetch_ivs(j + gridDim.x);
+            if (lo + kScanWindow >= n_pos) fetch_ivs(jn);
             depth += net_all;
             ups += tot_ud & 0xFFFFu;
             downs += tot_ud >> 16;
@@ -798,9 +812,23 @@ __global__ void __launch_bounds__(kSortThreads, 1) sort_kernel(DetectArgs a, Wor
         if (lane == 0) d = atomicAdd(dyn_cursor, 1.0);
         return d;
     };
-    auto to_item = [&](double d) { return d < (double)n_items ? __double2uint_rz(d) : n_items; };
-    auto draw_done = [&](double raw) { return __shfl_sync(FULL, to_item(raw), 0); };
-    uint32_t item = draw_done(draw_raw()), item1 = draw_done(draw_raw()), item2 = draw_done(draw_raw());
+    // A warp's first three batches are fixed: batch w * grid + b of each of the first three rounds for warp w of CTA b,
+    // so that the heaviest batches (the processing order starts with them) are spread evenly over the SMs and no
+    // start-up atomics are needed; the cursor deals everything behind them. (Drawing the three from the cursor back to
+    // back gave a warp three NEIGHBOURING heavy batches: +22 us on a 1/8 shard of C3.)
+    const uint32_t n_round = gridDim.x * kSortWarps, first = wid * gridDim.x + blockIdx.x;
+    const double n_fixed = (double)kFixedRounds * (double)n_round;
+    auto to_item = [&](double d) {
+        d += n_fixed;
+        return d < (double)n_items ? __double2uint_rz(d) : n_items;
+    };
+    uint32_t item = min(first, n_items), item1, item2;
+    if (kFixedRounds == 3u) {
+        item1 = min(n_round + first, n_items), item2 = min(2u * n_round + first, n_items);
+    } else {  // (one fixed round: the other two from the cursor, one after the other)
+        item1 = __shfl_sync(FULL, to_item(draw_raw()), 0);
+        item2 = __shfl_sync(FULL, to_item(draw_raw()), 0);
+    }
     // software pipeline: the record of batch i+2 is on its way to shared memory, the slab copies of batch i+1 are issued
     // as soon as the keys of batch i are in registers (one slab buffer) and land while batch i is sorted
     uint32_t cls0, cls1, cls2, s = 1;  // ws.rec[s]: record of batch i+1; ws.rec[s ^ 1]: of batch i+2
@@ -1519,12 +1547,26 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         // append to the staging buffer)
         forked = a.side_stream && a.ev_fork && a.ev_join && cudaEventRecord(a.ev_fork, stream) == cudaSuccess &&
                  cudaStreamWaitEvent(a.side_stream, a.ev_fork, 0) == cudaSuccess;
-        if (a.rows.n_scan) {  // short enough reads: begins and ends counted per position, depth scanned window by window
-            uint32_t grid = 2u * (uint32_t)dc->n_sm;
-            if (grid > a.rows.n_scan) grid = (uint32_t)a.rows.n_scan;
-            bigscan_kernel<<<grid, kScanThreads, kScanSmemBytes, forked ? a.side_stream : stream>>>(a, w, coverage);
+    }
+    {
+        // the register tier goes first: its persistent CTAs own a whole SM each and its first batches per warp are dealt
+        // by position, so it wants every SM from the start; the CTA tier's kernels deal their rows from a cursor and
+        // fill the SMs as the register tier leaves them
+        const ClassTab tab = make_plan(a);
+        const uint32_t items = tab.item_base[kNumClasses];
+        if (items) {
+            uint32_t grid = (uint32_t)dc->n_sm;
+            if (grid > items) grid = items;
+            if (a.validate) sort_kernel<true><<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage, pm);
+            else sort_kernel<false><<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage, pm);
             ++launches;
         }
+    }
+    if (a.rows.n_scan) {  // short enough reads: begins and ends counted per position, depth scanned window by window
+        uint32_t grid = 2u * (uint32_t)dc->n_sm;
+        if (grid > a.rows.n_scan) grid = (uint32_t)a.rows.n_scan;
+        bigscan_kernel<<<grid, kScanThreads, kScanSmemBytes, forked ? a.side_stream : stream>>>(a, w, coverage);
+        ++launches;
     }
     if (a.rows.n_big > a.rows.n_scan) {
         // the others are sorted: shared memory for the largest row (wide if any read is); rows beyond kCtaMaxSmemWords
@@ -1540,17 +1582,6 @@ int launch_detect(const DetectArgs &a, uint32_t coverage, double not_coverage, c
         ++launches;
     }
     if (forked && cudaEventRecord(a.ev_join, a.side_stream) != cudaSuccess) return -1;
-    {
-        const ClassTab tab = make_plan(a);
-        const uint32_t items = tab.item_base[kNumClasses];
-        if (items) {
-            uint32_t grid = (uint32_t)dc->n_sm;
-            if (grid > items) grid = items;
-            if (a.validate) sort_kernel<true><<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage, pm);
-            else sort_kernel<false><<<grid, kSortThreads, kSortSmemBytes, stream>>>(a, w, tab, coverage, pm);
-            ++launches;
-        }
-    }
     if (forked && cudaStreamWaitEvent(stream, a.ev_join, 0) != cudaSuccess) return -1;
     if (a.validate) {  // rows with a malformed interval: the reference's heap sweep itself, over what the kernels above listed
         literal_kernel<<<(uint32_t)dc->n_sm, 64, 0, stream>>>(a, w, coverage);

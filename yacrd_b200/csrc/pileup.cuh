@@ -27,6 +27,7 @@ enum Counter : uint32_t {
     kCntDone = 16,       // order_kernel: parts finished (the last one closes the step)
     kCntLiteral = 17,    // cursor over the list of malformed rows (literal heap sweep)
     kCntDynTicket = 18,  // (two words, a double) sort_kernel: cursor over the dynamically dealt batches
+    kCntScanTicket = 20, // bigscan_kernel: cursor over the rows of the scan list
     kCntHist = 32,       // kHistSlots x {NotBad, Chimeric, NotCovered}: the detect step's class histogram, striped
     kNumCounters = 32 + 3 * 32
 };
@@ -38,7 +39,8 @@ constexpr uint32_t kCntLiteralList = 2 * kNumCounters + 2;  // validating step: 
 constexpr uint32_t kCntMalformedIv = 2 * kNumCounters + 6;  // validating step: malformed intervals found so far
 constexpr uint32_t kCntLiteralLast = 2 * kNumCounters + 7;  // the two counts of the last finished validating step ...
 constexpr uint32_t kCntMalformedLast = 2 * kNumCounters + 9;  // ... (the closing CTA of order_kernel moves them here)
-constexpr uint32_t kCntScanList = 2 * kNumCounters + 4;     // upload: big rows of the position-scan path
+constexpr uint32_t kCntScanList = 2 * kNumCounters + 4;     // upload: big rows of the position-scan path, the heavy ones (filled from the front of the list)
+constexpr uint32_t kCntScanListBack = 2 * kNumCounters + 8; // ... and the light ones (filled from the back): bigscan_kernel takes the list in order, heavy rows first
 constexpr uint32_t kCntOrderTimeout = 2 * kNumCounters + 5; // order_kernel: the closing CTA gave up waiting for the others
 constexpr uint32_t kCntPeerTimeoutWait = 2 * kNumCounters + 3;  // peer_wait_kernel gave up (a rank died or never launched)
 constexpr uint32_t kCntClassCursor = 2 * kNumCounters + 10;  // upload: kNumClasses cursors of the worklist scatter
