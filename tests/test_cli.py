@@ -63,6 +63,20 @@ def test_cli_presets_match_the_oracle(tmp_path, c, n, golden):
 
 
 @pytest.mark.gpu
+def test_cli_ondisk_mode_streams_chunks_and_gives_the_same_report(tmp_path):
+    """`-d <prefix> --ondisk-buffer-size <bytes>` (cli.rs:61-70): here chunks of that many bytes of intervals go through the
+    device on the streamed path's lanes (chunks hold whole reads, a multiple of 1024 of them: the golden PAF's 230 reads
+    travel as one chunk); the report is the reference's."""
+    out = tmp_path / "out.yacrd"
+    r = run("-i", os.path.join(GOLDEN, "c1_overlaps.paf"), "-o", str(out), "-d", str(tmp_path / "ondisk"), "--ondisk-buffer-size", "8192")
+    assert r.returncode == 0, r.stderr
+    assert read_sorted_lines(str(out)) == read_sorted_lines(os.path.join(GOLDEN, "c1_truth.sorted.yacrd"))
+    assert not os.path.exists(str(tmp_path / "ondisk")), "nothing is written to disk"
+    r = run("-i", os.path.join(GOLDEN, "c1_overlaps.paf"), "-o", str(out), "-d", "x", "--ondisk-buffer-size", "abc")
+    assert r.returncode == 2
+
+
+@pytest.mark.gpu
 def test_cli_errors_like_the_reference(tmp_path):
     r = run("-i", str(tmp_path / "missing.paf"), "-o", str(tmp_path / "o.yacrd"))
     assert r.returncode == 1 and "Can't open file" in r.stderr                       # error.rs CantReadFile
