@@ -44,7 +44,8 @@ typedef enum yb_status {
                                           with the reference's own heap sweep, see yb_stats.n_malformed_intervals) */
     YB_ERR_INVALID_ARGUMENT = -9,
     YB_ERR_STATE = -10,                /* call order violated (e.g. results queried before compute) */
-    YB_ERR_TOO_LARGE = -11,            /* > 2^32-16 intervals or reads in one context, or a read longer than 2^31-1 */
+    YB_ERR_TOO_LARGE = -11,            /* > 2^32-16 intervals or reads in one context, a read longer than 2^31-1, or (yb_upload) a
+                                          one-shot batch of more than about 2.8e9 intervals + reads: use yb_set_chunk_intervals */
     YB_ERR_CUDA = -12,
     YB_ERR_NOMEM = -13
 } yb_status;
@@ -74,7 +75,7 @@ typedef struct yb_stats {
     uint64_t n_gaps;          /* after compute */
     uint64_t n_not_bad, n_chimeric, n_not_covered;
     uint64_t max_intervals_per_read;
-    uint64_t n_reads_warp, n_reads_cta, n_reads_huge; /* kernel tier each read took */
+    uint64_t n_reads_warp, n_reads_cta, n_reads_huge; /* reserved (always 0) */
     uint64_t kernel_launches; /* cumulative count of this library's kernel launches */
     uint64_t h2d_bytes, d2h_bytes; /* cumulative */
     uint64_t n_malformed_intervals; /* intervals with begin >= end or end > length in the last batch: accepted, like the

@@ -1259,7 +1259,7 @@ __global__ void __launch_bounds__(1024) row_stats_kernel(const uint32_t *__restr
 }
 
 // literal_kernel: the reference's algorithm itself (stack.rs:61-139: sort, min-heap sweep of the ends, head / tail
-// regions, merge of regions that share a begin), one thread per row, for the rows validate_kernel listed. It runs after
+// regions, merge of regions that share a begin), one thread per row, for the rows the validating kernels listed. It runs after
 // the sorting kernels and replaces what they staged for those rows. The row is sorted in place in the device copy of the
 // interval buffer (heapsort); the heap of ends and the regions live in a segment of the staging buffer.
 __device__ __forceinline__ bool lit_less(uint2 x, uint2 y) { return x.x != y.x ? x.x < y.x : x.y < y.y; }
