@@ -1210,7 +1210,8 @@ static int compute_streamed(yb_ctx *c, uint64_t coverage, double not_coverage) {
     int li = 0;
     while (r0 < n) {
         // the chunk ends at the first multiple of 1024 reads that holds chunk_intervals intervals (or at the end)
-        const uint32_t *stop = std::lower_bound(rp + r0 + 1, rp + n, rp[r0] + c->chunk_intervals);
+        const uint32_t target = (uint32_t)std::min<uint64_t>((uint64_t)rp[r0] + c->chunk_intervals, 0xFFFFFFFFull);
+        const uint32_t *stop = std::lower_bound(rp + r0 + 1, rp + n, target);
         uint32_t r1 = (uint32_t)(stop - rp);
         r1 = (uint32_t)std::min<uint64_t>(n, ((uint64_t)r1 + 1023u) & ~(uint64_t)1023u);
         if (fl[li].busy)
