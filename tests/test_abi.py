@@ -38,6 +38,21 @@ def test_product_does_not_link_or_import_the_oracle():
                 assert "yacrd_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
 
 
+def test_product_library_holds_no_measurement_code():
+    """The synthetic workload generator lives in workload/libyacrd_synth.so (both bench arms load it from there); the
+    product library exports only what include/yacrd_b200.h declares."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.split("\n") if " T " in l}
+    yb_syms = {s for s in exported if s.startswith("yb_")}
+    assert yb_syms == set(_declared_symbols()), yb_syms ^ set(_declared_symbols())
+    assert not [s for s in exported if "synth" in s or "oracle" in s]
+    import workload
+    W = workload.lib()
+    for name in ("yb_synth_count", "yb_synth_plan", "yb_synth_fill", "yb_synth_shard_of", "yb_synth_paf"):
+        assert hasattr(W, name)
+
+
 def test_version_and_names():
     assert yb.version().startswith("1.0.0 Magby")
     L = N.lib()
